@@ -1,0 +1,207 @@
+"""Batched planning on one GPU: the host side of the C ABI for many scenarios.
+
+    with DevicePlanner(config) as dp:
+        dp.load(scenarios)            # upload + rasterise (costmap.Map for every scenario)
+        res = dp.plan()               # PathPlanner.a_star_plan for every scenario, on the device
+
+`res` is a PlanResults: a structured numpy array of per-scenario summaries
+(hostcfg.SUMMARY_DTYPE), padded (n, cap_path, 3) paths and (n, cap_pops) pop-index traces.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .hostcfg import SUMMARY_DTYPE, STATUS_NAMES, make_avp_config
+from . import scenarios as scn
+
+
+class AvpError(RuntimeError):
+    pass
+
+
+@dataclass
+class PlanResults:
+    summaries: np.ndarray          # (n,) SUMMARY_DTYPE
+    paths: np.ndarray              # (n, cap_path, 3) f64, rows beyond n_final are unspecified
+    pops: Optional[np.ndarray]     # (n, cap_pops) i32 or None
+
+    def path(self, i: int) -> np.ndarray:
+        return self.paths[i, :min(int(self.summaries["n_final"][i]), self.paths.shape[1])]
+
+    def astar_path(self, i: int) -> np.ndarray:
+        return self.paths[i, :int(self.summaries["n_astar"][i])]
+
+    def pop_indices(self, i: int) -> np.ndarray:
+        return self.pops[i, :min(int(self.summaries["n_pops"][i]), self.pops.shape[1])]
+
+    def status_name(self, i: int) -> str:
+        return STATUS_NAMES.get(int(self.summaries["status"][i]), "?")
+
+    @property
+    def successors(self) -> int:
+        """collision-checked successor evaluations = sum of global_index (hybrid_a_star.py:239)"""
+        return int(self.summaries["global_index"].astype(np.int64).sum())
+
+
+def _dp(a):
+    return a.ctypes.data_as(_native.c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_native.c_ip)
+
+
+class DevicePlanner:
+    def __init__(self, config: dict = None, vehicle=None, device: int = 0, max_pops: int = 20000):
+        self._L = _native.lib()
+        self.cfg = make_avp_config(config, vehicle, max_pops=max_pops)
+        h = ctypes.c_void_p()
+        rc = self._L.avp_create(int(device), ctypes.byref(self.cfg), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise AvpError(f"avp_create failed (rc={rc}): no usable CUDA device {device}? this package has no CPU path")
+        self._h = h
+        self.n = 0
+        self.batch = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.avp_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise AvpError(f"{what} failed (rc={rc}): {self._L.avp_last_error(self._h).decode()}")
+
+    # -- scenarios / maps
+    def load(self, scenarios, rasterise: bool = True):
+        b = scenarios if isinstance(scenarios, scn.ScenarioBatch) else scn.pack(scenarios)
+        self.batch = b
+        self._ck(self._L.avp_scenarios_upload(self._h, len(b), _dp(b.poses), _ip(b.obs_off), _ip(b.nv), _ip(b.vert_off),
+                                              _dp(b.verts), _dp(b.boundary) if b.boundary is not None else None),
+                 "avp_scenarios_upload")
+        self.n = len(b)
+        self.h2d_bytes += b.nbytes()
+        if rasterise:
+            self._ck(self._L.avp_rasterise(self._h), "avp_rasterise")
+
+    def map_info(self, s: int):
+        dims = np.zeros(4, dtype=np.int32)
+        geom = np.zeros(6)
+        self._ck(self._L.avp_fetch_map(self._h, s, _ip(dims), _dp(geom), None, 0), "avp_fetch_map")
+        return dict(nx=int(dims[0]), ny=int(dims[1]), n_obs=int(dims[2]), raster_error=int(dims[3]),
+                    boundary=geom[:4].copy(), dx=float(geom[4]), dy=float(geom[5]))
+
+    def cost_map(self, s: int) -> np.ndarray:
+        info = self.map_info(s)
+        out = np.zeros(info["nx"] * info["ny"], dtype=np.uint8)
+        dims = np.zeros(4, dtype=np.int32)
+        geom = np.zeros(6)
+        self._ck(self._L.avp_fetch_map(self._h, s, _ip(dims), _dp(geom), out.ctypes.data_as(_native.c_u8p), out.size),
+                 "avp_fetch_map")
+        return out.reshape(info["nx"], info["ny"])
+
+    # -- leaf entry points
+    def check(self, s: int, poses) -> np.ndarray:
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        out = np.zeros(p.shape[0], dtype=np.uint8)
+        self._ck(self._L.avp_collision_check(self._h, s, p.shape[0], _dp(p), out.ctypes.data_as(_native.c_u8p)),
+                 "avp_collision_check")
+        return out.astype(bool)
+
+    def expand_pure(self, s: int, parent):
+        n = 2 * self.cfg.steering_angle_num
+        p = np.array(parent, dtype=np.float64)
+        pose = np.zeros((n, 3))
+        flags = np.zeros(n, dtype=np.int32)
+        rsl = np.zeros(n)
+        self._ck(self._L.avp_expand_pure(self._h, s, _dp(p), _dp(pose), _ip(flags), _dp(rsl)), "avp_expand_pure")
+        return pose, flags, rsl
+
+    def rs_optimal(self, q, maxc: float, step_size: float = 0.5, xy_np: int = 1, phi_np: int = 1, cap_pts: int = 256):
+        q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(-1, 6))
+        m = q.shape[0]
+        lengths = np.zeros((m, 5))
+        ct = ctypes.create_string_buffer(8 * m)
+        nseg = np.zeros(m, dtype=np.int32)
+        L = np.zeros(m)
+        x, y, yaw = np.zeros((m, cap_pts)), np.zeros((m, cap_pts)), np.zeros((m, cap_pts))
+        d = np.zeros((m, cap_pts), dtype=np.int32)
+        npts = np.zeros(m, dtype=np.int32)
+        self._ck(self._L.avp_rs_optimal(self._h, m, _dp(q), float(maxc), float(step_size), int(xy_np), int(phi_np),
+                                        _dp(lengths), ct, _ip(nseg), _dp(L), cap_pts, _dp(x), _dp(y), _dp(yaw), _ip(d),
+                                        _ip(npts)), "avp_rs_optimal")
+        names = [ct.raw[8 * i:8 * i + 8].split(b"\0")[0].decode() for i in range(m)]
+        return dict(nseg=nseg, lengths=lengths, ctypes=names, L=L, x=x, y=y, yaw=yaw, directions=d, n_pts=npts)
+
+    # -- whole searches
+    def plan(self, cap_path: int = 512, cap_pops: int = 0) -> PlanResults:
+        n = self.n
+        sums = np.zeros(n, dtype=SUMMARY_DTYPE)
+        paths = np.zeros((n, cap_path, 3))
+        pops = np.zeros((n, cap_pops), dtype=np.int32) if cap_pops > 0 else None
+        self._ck(self._L.avp_plan_batch(self._h, sums.ctypes.data_as(ctypes.c_void_p), _dp(paths), cap_path,
+                                        _ip(pops) if pops is not None else None, cap_pops), "avp_plan_batch")
+        self.d2h_bytes += sums.nbytes + paths.nbytes + (pops.nbytes if pops is not None else 0)
+        return PlanResults(sums, paths, pops)
+
+    def plan_resident(self, cap_path: int = 512, cap_pops: int = 0) -> float:
+        """Run the search with results left on the device; returns the CUDA-event time in ms."""
+        self._ck(self._L.avp_plan_configure(self._h, cap_path, cap_pops), "avp_plan_configure")
+        ms = ctypes.c_float()
+        self._ck(self._L.avp_plan_batch_resident(self._h, ctypes.byref(ms)), "avp_plan_batch_resident")
+        return float(ms.value)
+
+    def fetch(self, cap_path: int = 512, cap_pops: int = 0) -> PlanResults:
+        n = self.n
+        sums = np.zeros(n, dtype=SUMMARY_DTYPE)
+        paths = np.zeros((n, cap_path, 3))
+        pops = np.zeros((n, cap_pops), dtype=np.int32) if cap_pops > 0 else None
+        self._ck(self._L.avp_fetch_results(self._h, sums.ctypes.data_as(ctypes.c_void_p), _dp(paths), cap_path,
+                                           _ip(pops) if pops is not None else None, cap_pops), "avp_fetch_results")
+        return PlanResults(sums, paths, pops)
+
+    def result_device_pointers(self):
+        s, p = ctypes.c_void_p(), ctypes.c_void_p()
+        n, cp = ctypes.c_int64(), ctypes.c_int64()
+        self._ck(self._L.avp_result_device_buffer(self._h, ctypes.byref(s), ctypes.byref(p), ctypes.byref(n), ctypes.byref(cp)),
+                 "avp_result_device_buffer")
+        return s.value, p.value, n.value, cp.value
+
+    def hvalues(self, s: int) -> np.ndarray:
+        n_ids = ctypes.c_int64()
+        self._ck(self._L.avp_fetch_hvalues(self._h, s, None, 0, ctypes.byref(n_ids)), "avp_fetch_hvalues")
+        out = np.zeros(n_ids.value, dtype=np.int32)
+        self._ck(self._L.avp_fetch_hvalues(self._h, s, _ip(out), out.size, ctypes.byref(n_ids)), "avp_fetch_hvalues")
+        return out
+
+    def hq_log(self, s: int, n_hq: int) -> np.ndarray:
+        out = np.zeros((256, 3), dtype=np.int32)
+        self._ck(self._L.avp_fetch_hq_log(self._h, s, _ip(out), 256), "avp_fetch_hq_log")
+        return out[:min(n_hq, 256)]
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.avp_launch_count(self._h))
+
+    def device_info(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self._L.avp_device_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return dict(n_sm=a.value, slots=b.value, block=c.value)

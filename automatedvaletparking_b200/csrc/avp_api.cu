@@ -1,0 +1,400 @@
+// avp_api.cu -- host side of the C ABI declared in include/avp_b200.h.
+// Plain CUDA runtime; no torch types.  There is no CPU fallback: every entry point that
+// computes launches a kernel on the context's device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "avp_kernels.cuh"
+
+struct avp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  avp_config cfg;
+  std::string err;
+  int64_t launches = 0;
+  int n_sm = 0, slots = 0;
+  // scenarios
+  int n = 0;
+  std::vector<ScenDev> h_scen;
+  ScenDev *d_scen = nullptr;
+  int32_t *d_nv = nullptr, *d_vert_off = nullptr; double *d_verts = nullptr;
+  uint8_t *d_cost = nullptr; int64_t cost_bytes = 0;
+  int32_t *d_col = nullptr; int64_t col_count = 0;
+  double2 *d_cells = nullptr; int64_t cell_count = 0;
+  bool rasterised = false;
+  // per-id arrays
+  int64_t id_count = 0;
+  int32_t *d_hval = nullptr, *d_ost = nullptr; double *d_gx = nullptr, *d_gy = nullptr;
+  // per-slot workspaces
+  int ws_slots = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
+  Node *d_nodes = nullptr; int32_t *d_oheap = nullptr, *d_htab = nullptr; unsigned long long *d_dheap = nullptr;
+  double *d_course = nullptr; int32_t *d_course_dir = nullptr;
+  // results
+  avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
+  int cap_path = 0, cap_pops = 0; int res_n = 0;
+  int *d_counter = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch for the small API kernels
+  void *d_scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
+#define FAIL(msg) do { ctx->err = (msg); return -2; } while (0)
+
+static void free_dev(void *p) { if (p) cudaFree(p); }
+
+static int ensure_scratch(avp_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return 0;
+  free_dev(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+  CK(cudaMalloc(&ctx->d_scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return 0;
+}
+
+extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
+  if (!cfg || !out) return -3;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return -4;      // no CUDA device: fail loudly
+  if (device_id < 0 || device_id >= ndev) return -5;
+  if (cfg->steering_angle_num < 1 || 2 * cfg->steering_angle_num > AVP_NCHILD_MAX) return -6;
+  avp_ctx *ctx = new avp_ctx();
+  ctx->device = device_id; ctx->cfg = *cfg;
+  if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return -7; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return -8; }
+  ctx->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, AVP_BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  ctx->slots = ctx->n_sm * per_sm;               // persistent grid: a multiple of the SM count
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
+  *out = ctx;
+  return 0;
+}
+
+static void free_scenarios(avp_ctx *ctx) {
+  free_dev(ctx->d_scen); free_dev(ctx->d_nv); free_dev(ctx->d_vert_off); free_dev(ctx->d_verts); free_dev(ctx->d_cost);
+  free_dev(ctx->d_col); free_dev(ctx->d_cells); free_dev(ctx->d_hval); free_dev(ctx->d_ost); free_dev(ctx->d_gx); free_dev(ctx->d_gy);
+  ctx->d_scen = nullptr; ctx->d_nv = ctx->d_vert_off = nullptr; ctx->d_verts = nullptr; ctx->d_cost = nullptr; ctx->d_col = nullptr;
+  ctx->d_cells = nullptr; ctx->d_hval = ctx->d_ost = nullptr; ctx->d_gx = ctx->d_gy = nullptr;
+  ctx->n = 0; ctx->rasterised = false;
+}
+static void free_results(avp_ctx *ctx) {
+  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq);
+  ctx->d_sums = nullptr; ctx->d_paths = nullptr; ctx->d_pops = nullptr; ctx->d_hq = nullptr; ctx->res_n = 0;
+}
+static void free_ws(avp_ctx *ctx) {
+  free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir);
+  ctx->d_nodes = nullptr; ctx->d_oheap = ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
+}
+
+extern "C" int avp_destroy(avp_ctx *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_scenarios(ctx); free_results(ctx); free_ws(ctx);
+  free_dev(ctx->d_counter); free_dev(ctx->d_scratch);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" const char *avp_last_error(const avp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t avp_launch_count(const avp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, const int32_t *obs_off, const int32_t *nv,
+                                    const int32_t *vert_off, const double *verts, const double *boundary_override) {
+  if (!ctx) return -3;
+  if (n <= 0 || !poses || !obs_off) FAIL("avp_scenarios_upload: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  free_scenarios(ctx);
+  const double ds = ctx->cfg.map_discrete_size;
+  ctx->h_scen.assign(n, ScenDev());
+  int64_t cost_off = 0, col_off = 0, id_off = 0;
+  for (int i = 0; i < n; ++i) {
+    ScenDev &S = ctx->h_scen[i];
+    memset(&S, 0, sizeof(S));
+    memcpy(S.pose, poses + 6 * i, 6 * sizeof(double));
+    if (boundary_override) memcpy(S.b, boundary_override + 4 * i, 4 * sizeof(double));
+    else {                                                       // costmap.py:143-146, :169-172
+      const double x0 = S.pose[0], y0 = S.pose[1], xf = S.pose[3], yf = S.pose[4];
+      S.b[0] = floor((x0 < xf ? x0 : xf) - 12); S.b[1] = floor((x0 > xf ? x0 : xf) + 12);
+      S.b[2] = floor((y0 < yf ? y0 : yf) - 12); S.b[3] = floor((y0 > yf ? y0 : yf) + 12);
+    }
+    S.nx = (int)((S.b[1] - S.b[0]) / ds); S.ny = (int)((S.b[3] - S.b[2]) / ds);           // costmap.py:182-185
+    if (S.nx < 3 || S.ny < 3 || S.nx > 16384 || S.ny > 16384) FAIL("avp_scenarios_upload: map extent out of range");
+    S.stepx = (S.b[1] - S.b[0]) / (S.nx - 1); S.stepy = (S.b[3] - S.b[2]) / (S.ny - 1);   // np.linspace step
+    volatile double x1 = 1.0 * S.stepx, y1 = 1.0 * S.stepy; x1 = x1 + S.b[0]; y1 = y1 + S.b[2];
+    S.dx = x1 - S.b[0]; S.dy = y1 - S.b[2];                                                  // costmap.py:190-191
+    S.stride = (int)((S.b[1] - S.b[0]) / S.dx); S.mx = S.stride; S.my = (int)((S.b[3] - S.b[2]) / S.dy);
+    const long W = (long)floor((S.b[1] - S.b[0]) / S.dx) + 2, H = (long)floor((S.b[3] - S.b[2]) / S.dy) + 2;
+    S.n_ids = (int32_t)(H * S.stride + W + 8);
+    S.obs_begin = obs_off[i]; S.obs_end = obs_off[i + 1];
+    S.cost_off = cost_off; cost_off += (int64_t)S.nx * S.ny; cost_off = (cost_off + 15) & ~15ll;
+    S.col_off = col_off; col_off += S.nx + 1;
+    S.id_off = id_off; id_off += (S.n_ids + 3) & ~3;
+  }
+  ctx->n = n; ctx->cost_bytes = cost_off; ctx->col_count = col_off; ctx->id_count = id_off;
+  const int n_poly = obs_off[n];
+  const int n_vert = n_poly > 0 ? vert_off[n_poly] : 0;
+  CK(cudaMalloc(&ctx->d_scen, sizeof(ScenDev) * n));
+  CK(cudaMalloc(&ctx->d_nv, sizeof(int32_t) * (n_poly + 1)));
+  CK(cudaMalloc(&ctx->d_vert_off, sizeof(int32_t) * (n_poly + 1)));
+  CK(cudaMalloc(&ctx->d_verts, sizeof(double) * 2 * (n_vert + 1)));
+  CK(cudaMalloc(&ctx->d_cost, (size_t)cost_off + 16));
+  CK(cudaMalloc(&ctx->d_col, sizeof(int32_t) * (col_off + 1)));
+  CK(cudaMalloc(&ctx->d_hval, sizeof(int32_t) * id_off));
+  CK(cudaMalloc(&ctx->d_ost, sizeof(int32_t) * id_off));
+  CK(cudaMalloc(&ctx->d_gx, sizeof(double) * id_off));
+  CK(cudaMalloc(&ctx->d_gy, sizeof(double) * id_off));
+  CK(cudaMemcpyAsync(ctx->d_scen, ctx->h_scen.data(), sizeof(ScenDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_poly > 0) {
+    CK(cudaMemcpyAsync(ctx->d_nv, nv, sizeof(int32_t) * n_poly, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_vert_off, vert_off, sizeof(int32_t) * (n_poly + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_verts, verts, sizeof(double) * 2 * n_vert, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int avp_rasterise(avp_ctx *ctx) {
+  if (!ctx) return -3;
+  if (ctx->n <= 0) FAIL("avp_rasterise: no scenarios uploaded");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n;
+  CK(cudaMemsetAsync(ctx->d_cost, 0, (size_t)ctx->cost_bytes, ctx->stream));
+  k_raster<<<n, 64, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_nv, ctx->d_vert_off, ctx->d_verts, ctx->d_cost); ctx->launches++;
+  k_count_cols<<<n, 128, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_cost, ctx->d_col); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_scen.data(), ctx->d_scen, sizeof(ScenDev) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int64_t cell_off = 0;
+  for (int i = 0; i < n; ++i) { ScenDev &S = ctx->h_scen[i]; S.cell_off = cell_off; S.cell_cap = S.n_obs; cell_off += (S.n_obs + 1) & ~1; }
+  ctx->cell_count = cell_off;
+  free_dev(ctx->d_cells); ctx->d_cells = nullptr;
+  CK(cudaMalloc(&ctx->d_cells, sizeof(double2) * (cell_off + 1)));
+  CK(cudaMemcpyAsync(ctx->d_scen, ctx->h_scen.data(), sizeof(ScenDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_fill_cells<<<n, 128, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_cost, ctx->d_col, ctx->d_cells); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->rasterised = true;
+  return 0;
+}
+
+extern "C" int avp_fetch_map(avp_ctx *ctx, int s, int32_t *dims, double *geom, uint8_t *cost_map, int64_t cap) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n) FAIL("avp_fetch_map: scenario index out of range");
+  if (!ctx->rasterised) FAIL("avp_fetch_map: call avp_rasterise first");
+  CK(cudaSetDevice(ctx->device));
+  const ScenDev &S = ctx->h_scen[s];
+  if (dims) { dims[0] = S.nx; dims[1] = S.ny; dims[2] = S.n_obs; dims[3] = S.raster_error; }
+  if (geom) { memcpy(geom, S.b, 4 * sizeof(double)); geom[4] = S.dx; geom[5] = S.dy; }
+  if (cost_map) {
+    if (cap < (int64_t)S.nx * S.ny) FAIL("avp_fetch_map: buffer too small");
+    CK(cudaMemcpyAsync(cost_map, ctx->d_cost + S.cost_off, (size_t)S.nx * S.ny, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int avp_collision_check(avp_ctx *ctx, int s, int m, const double *poses, uint8_t *out) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n || m < 0) FAIL("avp_collision_check: bad arguments");
+  if (!ctx->rasterised) FAIL("avp_collision_check: call avp_rasterise first");
+  if (m == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t pb = sizeof(double) * 3 * m;
+  if (ensure_scratch(ctx, pb + m + 64)) return -1;
+  double *d_p = (double *)ctx->d_scratch; uint8_t *d_o = (uint8_t *)ctx->d_scratch + pb;
+  CK(cudaMemcpyAsync(d_p, poses, pb, cudaMemcpyHostToDevice, ctx->stream));
+  const int wpb = 4, blocks = (m + wpb - 1) / wpb;
+  k_check_batch<<<blocks, wpb * 32, 0, ctx->stream>>>(ctx->cfg, ctx->d_scen, s, ctx->d_cells, ctx->d_col, m, d_p, d_o); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_o, m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int avp_expand_pure(avp_ctx *ctx, int s, const double parent_pose[3], double *out_pose, int32_t *out_flags, double *out_rsL) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n) FAIL("avp_expand_pure: scenario index out of range");
+  if (!ctx->rasterised) FAIL("avp_expand_pure: call avp_rasterise first");
+  CK(cudaSetDevice(ctx->device));
+  const int nc = 2 * ctx->cfg.steering_angle_num;
+  if (ensure_scratch(ctx, sizeof(double) * 4 * nc + sizeof(int32_t) * nc + 64)) return -1;
+  double *d_pose = (double *)ctx->d_scratch, *d_L = d_pose + 3 * nc; int32_t *d_fl = (int32_t *)(d_L + nc);
+  k_expand_pure<<<1, nc * 32, 0, ctx->stream>>>(ctx->cfg, ctx->d_scen, s, ctx->d_cells, ctx->d_col, parent_pose[0], parent_pose[1], parent_pose[2], d_pose, d_fl, d_L);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_pose, d_pose, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_rsL, d_L, sizeof(double) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_flags, d_fl, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int avp_rs_optimal(avp_ctx *ctx, int m, const double *q, double maxc, double step_size, int xy_np, int phi_np,
+                              double *lengths, char *ctypes, int32_t *nseg, double *L, int cap_pts,
+                              double *x, double *y, double *yaw, int32_t *dir, int32_t *n_pts) {
+  if (!ctx) return -3;
+  if (m <= 0 || cap_pts <= 0) FAIL("avp_rs_optimal: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  size_t off = 0; auto take = [&](size_t b) { size_t o = off; off += (b + 15) & ~(size_t)15; return o; };
+  const size_t o_q = take(sizeof(double) * 6 * m), o_len = take(sizeof(double) * 5 * m), o_ct = take(8 * (size_t)m), o_ns = take(4 * (size_t)m),
+               o_L = take(8 * (size_t)m), o_x = take(8 * (size_t)m * cap_pts), o_y = take(8 * (size_t)m * cap_pts), o_yaw = take(8 * (size_t)m * cap_pts),
+               o_dir = take(4 * (size_t)m * cap_pts), o_np = take(4 * (size_t)m);
+  if (ensure_scratch(ctx, off + 64)) return -1;
+  char *B = (char *)ctx->d_scratch;
+  CK(cudaMemcpyAsync(B + o_q, q, sizeof(double) * 6 * m, cudaMemcpyHostToDevice, ctx->stream));
+  k_rs_optimal<<<(m + 3) / 4, 128, 0, ctx->stream>>>(m, (double *)(B + o_q), maxc, step_size, xy_np, phi_np, (double *)(B + o_len), B + o_ct, (int32_t *)(B + o_ns),
+                                                      (double *)(B + o_L), cap_pts, (double *)(B + o_x), (double *)(B + o_y), (double *)(B + o_yaw),
+                                                      (int32_t *)(B + o_dir), (int32_t *)(B + o_np));
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(lengths, B + o_len, sizeof(double) * 5 * m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctypes, B + o_ct, 8 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nseg, B + o_ns, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(L, B + o_L, 8 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(x, B + o_x, 8 * (size_t)m * cap_pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(y, B + o_y, 8 * (size_t)m * cap_pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(yaw, B + o_yaw, 8 * (size_t)m * cap_pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(dir, B + o_dir, 4 * (size_t)m * cap_pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(n_pts, B + o_np, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int ensure_ws(avp_ctx *ctx) {
+  const int nchild = 2 * ctx->cfg.steering_angle_num;
+  const int max_pops = ctx->cfg.max_pops > 0 ? ctx->cfg.max_pops : 20000;
+  const int node_cap = nchild * (max_pops + 1) + 2;
+  int slots = ctx->slots; if (slots > ctx->n) slots = ctx->n;      // no more CTAs than scenarios
+  if (ctx->ws_slots >= slots && ctx->node_cap == node_cap) return 0;
+  free_ws(ctx);
+  int hb = 1; while (hb < 2 * node_cap) hb <<= 1;
+  ctx->node_cap = node_cap; ctx->htab_size = hb; ctx->dheap_cap = 1 << 16;
+  const int S = ctx->slots;   // allocate for the full persistent grid once
+  CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)S * node_cap));
+  CK(cudaMalloc(&ctx->d_oheap, sizeof(int32_t) * (size_t)S * node_cap));
+  CK(cudaMalloc(&ctx->d_htab, sizeof(int32_t) * (size_t)S * hb));
+  CK(cudaMalloc(&ctx->d_dheap, sizeof(unsigned long long) * (size_t)S * ctx->dheap_cap));
+  CK(cudaMalloc(&ctx->d_course, sizeof(double) * (size_t)S * 3 * AVP_COURSE_CAP));
+  CK(cudaMalloc(&ctx->d_course_dir, sizeof(int32_t) * (size_t)S * AVP_COURSE_CAP));
+  ctx->ws_slots = S;
+  return 0;
+}
+
+static int ensure_results(avp_ctx *ctx, int cap_path, int cap_pops) {
+  if (ctx->res_n == ctx->n && ctx->cap_path == cap_path && ctx->cap_pops == cap_pops) return 0;
+  free_results(ctx);
+  const size_t n = ctx->n;
+  CK(cudaMalloc(&ctx->d_sums, sizeof(avp_plan_summary) * n));
+  CK(cudaMalloc(&ctx->d_paths, sizeof(double) * n * cap_path * 3));
+  CK(cudaMalloc(&ctx->d_pops, sizeof(int32_t) * n * (size_t)(cap_pops > 0 ? cap_pops : 1)));
+  CK(cudaMalloc(&ctx->d_hq, sizeof(int32_t) * n * AVP_HQ_CAP * 3));
+  ctx->res_n = ctx->n; ctx->cap_path = cap_path; ctx->cap_pops = cap_pops;
+  return 0;
+}
+
+static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
+  if (ctx->n <= 0) FAIL("plan: no scenarios uploaded");
+  if (!ctx->rasterised) FAIL("plan: call avp_rasterise first");
+  CK(cudaSetDevice(ctx->device));
+  if (ensure_ws(ctx)) return -1;
+  KParams P; memset(&P, 0, sizeof(P));
+  P.cfg = ctx->cfg; if (P.cfg.max_pops <= 0) P.cfg.max_pops = 20000;
+  P.n_scen = ctx->n; P.scen = ctx->d_scen; P.cost = ctx->d_cost; P.cells = ctx->d_cells; P.col_start = ctx->d_col;
+  P.hval = ctx->d_hval; P.ost = ctx->d_ost; P.gx = ctx->d_gx; P.gy = ctx->d_gy;
+  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap;
+  P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
+  P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
+  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter;
+  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_search<<<grid, AVP_BLOCK, 0, ctx->stream>>>(P); ctx->launches++;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+extern "C" int avp_fetch_results(avp_ctx *ctx, avp_plan_summary *summaries, double *final_path, int cap_path, int32_t *pops, int cap_pops) {
+  if (!ctx) return -3;
+  if (ctx->res_n != ctx->n || !ctx->d_sums) FAIL("avp_fetch_results: no results");
+  if (cap_path != ctx->cap_path || (pops && cap_pops != ctx->cap_pops)) FAIL("avp_fetch_results: capacities differ from the plan call");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n;
+  if (summaries) CK(cudaMemcpyAsync(summaries, ctx->d_sums, sizeof(avp_plan_summary) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (final_path) CK(cudaMemcpyAsync(final_path, ctx->d_paths, sizeof(double) * n * cap_path * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pops && cap_pops > 0) CK(cudaMemcpyAsync(pops, ctx->d_pops, sizeof(int32_t) * n * cap_pops, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int avp_plan_configure(avp_ctx *ctx, int cap_path, int cap_pops) {
+  if (!ctx) return -3;
+  if (cap_path <= 0 || cap_pops < 0) FAIL("avp_plan_configure: bad capacities");
+  CK(cudaSetDevice(ctx->device));
+  return ensure_results(ctx, cap_path, cap_pops);
+}
+
+extern "C" int avp_plan_batch(avp_ctx *ctx, avp_plan_summary *summaries, double *final_path, int cap_path, int32_t *pops, int cap_pops) {
+  if (!ctx) return -3;
+  if (cap_path <= 0) FAIL("avp_plan_batch: cap_path must be positive");
+  CK(cudaSetDevice(ctx->device));
+  if (ensure_results(ctx, cap_path, pops ? cap_pops : 0)) return -1;
+  int rc = launch_search(ctx, nullptr);
+  if (rc) return rc;
+  return avp_fetch_results(ctx, summaries, final_path, cap_path, pops, pops ? cap_pops : 0);
+}
+
+extern "C" int avp_plan_batch_resident(avp_ctx *ctx, float *elapsed_ms) {
+  if (!ctx) return -3;
+  if (ctx->res_n != ctx->n || !ctx->d_sums) { if (ensure_results(ctx, ctx->cap_path > 0 ? ctx->cap_path : 512, ctx->cap_pops)) return -1; }
+  return launch_search(ctx, elapsed_ms);
+}
+
+extern "C" int avp_result_device_buffer(avp_ctx *ctx, void **sums, void **paths, int64_t *n, int64_t *cap_path) {
+  if (!ctx) return -3;
+  if (ctx->res_n != ctx->n || !ctx->d_sums) FAIL("avp_result_device_buffer: no results");
+  if (sums) *sums = ctx->d_sums; if (paths) *paths = ctx->d_paths; if (n) *n = ctx->n; if (cap_path) *cap_path = ctx->cap_path;
+  return 0;
+}
+
+extern "C" int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *n_ids) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n) FAIL("avp_fetch_hvalues: scenario index out of range");
+  CK(cudaSetDevice(ctx->device));
+  const ScenDev &S = ctx->h_scen[s];
+  if (n_ids) *n_ids = S.n_ids;
+  if (hval) {
+    if (cap < S.n_ids) FAIL("avp_fetch_hvalues: buffer too small");
+    CK(cudaMemcpyAsync(hval, ctx->d_hval + S.id_off, sizeof(int32_t) * S.n_ids, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int avp_fetch_hq_log(avp_ctx *ctx, int s, int32_t *log3, int cap_entries) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n || !ctx->d_hq) FAIL("avp_fetch_hq_log: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int m = cap_entries < AVP_HQ_CAP ? cap_entries : AVP_HQ_CAP;
+  CK(cudaMemcpyAsync(log3, ctx->d_hq + (size_t)s * AVP_HQ_CAP * 3, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block) {
+  if (!ctx) return -3;
+  if (n_sm) *n_sm = ctx->n_sm; if (slots) *slots = ctx->slots; if (block) *block = AVP_BLOCK;
+  return 0;
+}

@@ -1,0 +1,529 @@
+// avp_dev.cuh -- device-side building blocks of the hybrid-A* hot path (sm_100a).
+//
+// Everything here is fp64 IEEE arithmetic evaluated in the reference's operation order;
+// the file is compiled with -fmad=false and every fused multiply-add is explicit.
+// Citations are to the reference (wenqing-2021/AutomatedValetParking) file:line.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/avp_b200.h"
+#include "avp_sincos.h"
+
+#define AVP_PI 3.141592653589793  /* math.pi (rs_curve.py:25) */
+#define AVP_HALF_PI (0.5 * AVP_PI)
+#define AVP_FULL_MASK 0xffffffffu
+#define AVP_MAX_VERT 64           /* vertices per obstacle polygon handled by the rasteriser */
+
+// ------------------------------------------------------------------------------------------
+// per-scenario device record
+struct ScenDev {
+  double pose[6];        // x0,y0,theta0,xf,yf,thetaf
+  double b[4];           // boundary (costmap.py:169-172)
+  double dx, dy;         // _discrete_x/_y (costmap.py:190-191)
+  double stepx, stepy;   // np.linspace step (b1-b0)/(nx-1)
+  int32_t nx, ny;        // cost_map.shape
+  int32_t stride;        // int((b1-b0)/dx): row stride of convert_position_to_index (costmap.py:327-328)
+  int32_t mx, my;        // is_obstacle clamp (compute_h.py:243-246)
+  int32_t n_ids;         // size of the per-id arrays
+  int32_t n_obs;         // count(cost_map == 255)
+  int32_t raster_error;
+  int64_t cost_off;      // into cost maps (bytes)
+  int64_t cell_off;      // into obstacle cell list (double2 entries)
+  int64_t col_off;       // into column starts (int32 entries, nx+1 per scenario)
+  int64_t id_off;        // into per-id arrays
+  int32_t cell_cap;      // capacity of the cell list
+  int32_t obs_begin, obs_end;  // polygons of this scenario
+};
+
+// ------------------------------------------------------------------------------------------
+// small math helpers
+
+__device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double d_mul(double a, double b) { return __dmul_rn(a, b); }
+
+// math.hypot of CPython 3.12 (Modules/mathmodule.c vector_norm, n = 2) -- used by rs_curve.R
+// (rs_curve.py:659-666).  Scaling by a power of two is exact; Dekker products; compensated sum.
+struct dl_t { double hi, lo; };
+__device__ __forceinline__ dl_t dl_fast_sum(double a, double b) { dl_t r; r.hi = a + b; r.lo = (a - r.hi) + b; return r; }
+__device__ __forceinline__ dl_t dl_split(double x) { double t = x * 134217729.0; dl_t r; r.hi = t - (t - x); r.lo = x - r.hi; return r; }
+__device__ __forceinline__ dl_t dl_mul(double x, double y) {
+  dl_t xx = dl_split(x), yy = dl_split(y);
+  double p = xx.hi * yy.hi, q = xx.hi * yy.lo + xx.lo * yy.hi;
+  dl_t r; r.hi = p + q; r.lo = p - r.hi + q + xx.lo * yy.lo; return r;
+}
+__device__ __noinline__ double py_hypot(double a, double b) {
+  double v0 = fabs(a), v1 = fabs(b);
+  double mx = v0 > v1 ? v0 : v1;
+  if (isinf(v0) || isinf(v1)) return INFINITY;
+  if (isnan(v0) || isnan(v1)) return NAN;
+  if (mx == 0.0) return mx;
+  int max_e; frexp(mx, &max_e);
+  if (max_e < -1023) return 2.2250738585072014e-308 * py_hypot(v0 / 2.2250738585072014e-308, v1 / 2.2250738585072014e-308);
+  double scale = ldexp(1.0, -max_e), csum = 1.0, frac1 = 0.0, frac2 = 0.0, x, h;
+  dl_t pr, sm;
+  x = v0 * scale; pr = dl_mul(x, x); sm = dl_fast_sum(csum, pr.hi); csum = sm.hi; frac1 += pr.lo; frac2 += sm.lo;
+  x = v1 * scale; pr = dl_mul(x, x); sm = dl_fast_sum(csum, pr.hi); csum = sm.hi; frac1 += pr.lo; frac2 += sm.lo;
+  h = sqrt(csum - 1.0 + (frac1 + frac2));
+  pr = dl_mul(-h, h); sm = dl_fast_sum(csum, pr.hi); csum = sm.hi; frac1 += pr.lo; frac2 += sm.lo;
+  x = csum - 1.0 + (frac1 + frac2);
+  h += x / (2.0 * h);
+  return h / scale;
+}
+
+// Python float % (Objects/floatobject.c float_rem); fmod is exact
+__device__ __forceinline__ double py_mod(double v, double w) {
+  double m = fmod(v, w);
+  if (m != 0.0) { if ((w < 0) != (m < 0)) m += w; } else m = copysign(0.0, w);
+  return m;
+}
+
+// CPython 3.12 sum() over a list whose element i is an np.float64 iff bit i of npmask is set
+// (see oracle/avp_oracle.c py_sum for the derivation)
+__device__ __forceinline__ double py_sum(const double *v, int n, unsigned npmask) {
+  double f = 0.0 + v[0], c = 0.0;
+  int i = 1;
+  if (!(npmask & 1u)) {
+    for (; i < n && !(npmask & (1u << i)); ++i) {
+      double x = v[i], t = f + x;
+      if (fabs(f) >= fabs(x)) c += (f - t) + x; else c += (x - t) + f;
+      f = t;
+    }
+    if (c != 0.0 && isfinite(c)) f += c;
+  }
+  for (; i < n; ++i) f = f + v[i];
+  return f;
+}
+
+// rs_curve.py:649-656
+__device__ __forceinline__ double pi_2_pi(double th) {
+  while (th > AVP_PI) th -= 2.0 * AVP_PI;
+  while (th < -AVP_PI) th += 2.0 * AVP_PI;
+  return th;
+}
+// rs_curve.py:669-680
+__device__ __forceinline__ double rs_M(double th) {
+  double phi = py_mod(th, 2.0 * AVP_PI);
+  if (phi < -AVP_PI) phi += 2.0 * AVP_PI;
+  if (phi > AVP_PI) phi -= 2.0 * AVP_PI;
+  return phi;
+}
+
+// np.linspace(b0, b1, n)[k] (numpy/_core/function_base.py): k*step + start, last element = stop
+__device__ __forceinline__ double lin_at(double start, double stop, double step, int n, int k) {
+  return (k == n - 1) ? stop : d_add(d_mul((double)k, step), start);
+}
+
+// Map.convert_position_to_index (costmap.py:319-329)
+__device__ __forceinline__ long long map_index(const ScenDev &S, double gx, double gy) {
+  long long i0 = (long long)floor((gx - S.b[0]) / S.dx);
+  long long i1 = (long long)floor((S.b[3] - gy) / S.dy) * (long long)S.stride;
+  return i0 + i1;
+}
+
+// ------------------------------------------------------------------------------------------
+// collision check (collision_check/collision_check.py)
+
+struct VehGeom {
+  double vb[5][2];       // create_anticlockpoint corners (costmap.py:85-121)
+  double x_min, x_max, y_min, y_max;
+  double v_lb, v_len;
+  double lk[4], lb[4], ls[4];   // slope, intercept, sqrt(1+k^2) of the 4 boundary lines
+};
+
+__device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y, double th, VehGeom &g) {
+  const double cs = avp_cos(th), sn = avp_sin(th);
+  const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
+  const double lx0 = -c.lr - fr, lx1 = c.lw + c.lf + fr, ly0 = -c.lb / 2 - sd, ly1 = c.lb / 2 + sd;
+  const double locx[4] = {lx0, lx1, lx1, lx0}, locy[4] = {ly0, ly0, ly1, ly1};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    // trans_matrix.transpose().dot(local) + [x, y]; BLAS gemv row = fma(A[r][1], v1, A[r][0]*v0)
+    g.vb[i][0] = __fma_rn(-sn, locy[i], cs * locx[i]) + x;
+    g.vb[i][1] = __fma_rn(cs, locy[i], sn * locx[i]) + y;
+  }
+  g.vb[4][0] = g.vb[0][0]; g.vb[4][1] = g.vb[0][1];
+  g.x_max = g.x_min = g.vb[0][0]; g.y_max = g.y_min = g.vb[0][1];
+#pragma unroll
+  for (int i = 1; i < 5; ++i) {
+    if (g.vb[i][0] > g.x_max) g.x_max = g.vb[i][0]; if (g.vb[i][0] < g.x_min) g.x_min = g.vb[i][0];
+    if (g.vb[i][1] > g.y_max) g.y_max = g.vb[i][1]; if (g.vb[i][1] < g.y_min) g.y_min = g.vb[i][1];
+  }
+  double d0 = g.vb[0][0] - g.vb[3][0], d1 = g.vb[0][1] - g.vb[3][1];
+  g.v_lb = sqrt(d0 * d0 + d1 * d1);                                   // collision_check.py:165-166
+  d0 = g.vb[3][0] - g.vb[2][0]; d1 = g.vb[3][1] - g.vb[2][1];
+  g.v_len = sqrt(d0 * d0 + d1 * d1);                                  // :168-169
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                                       // :149-155, :180-190
+    const double *p1 = g.vb[i], *p2 = g.vb[(i < 3) ? i + 1 : 0];
+    g.lk[i] = (p2[1] - p1[1]) / (p2[0] - p1[0]);
+    g.lb[i] = p1[1] - g.lk[i] * p1[0];
+    g.ls[i] = sqrt(1 + g.lk[i] * g.lk[i]);
+  }
+}
+
+// the per-cell predicate of distance_checker.check (collision_check.py:197-238)
+__device__ __forceinline__ bool cell_hits(const VehGeom &g, double ox, double oy) {
+  double dis[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dis[i] = fabs(g.lk[i] * ox + g.lb[i] - oy) / g.ls[i];
+  const bool c1 = fabs(dis[0] - dis[2]) < g.v_lb - 0.01;
+  const bool c2 = fabs(dis[1] - dis[3]) < g.v_len - 0.01;
+  if (c1 && c2) return true;
+  bool on_x = false, on_y = false;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) on_x |= (ox == g.vb[i][0]);
+  if (on_x) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) on_y |= (oy == g.vb[i][1]);
+  }
+  if (on_x && on_y) return true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double k1 = (g.vb[i][1] - oy) / (g.vb[i][0] - ox);
+    if (k1 == g.lk[i]) return true;
+  }
+  return false;
+}
+
+// Column range [lo, hi] of raster columns whose x position lies in [x_min, x_max]
+// (the inclusive AABB filter of get_near_obstacles, collision_check.py:60-63, applied to
+// the np.where order, which is sorted by column).
+__device__ __forceinline__ void col_range(const ScenDev &S, double x_min, double x_max, int &lo, int &hi) {
+  const int nx = S.nx;
+  int a = (int)floor((x_min - S.b[0]) / S.stepx) - 1; if (a < 0) a = 0; if (a > nx - 1) a = nx - 1;
+  while (a > 0 && lin_at(S.b[0], S.b[1], S.stepx, nx, a - 1) >= x_min) --a;
+  while (a < nx && !(lin_at(S.b[0], S.b[1], S.stepx, nx, a) >= x_min)) ++a;
+  int b = (int)floor((x_max - S.b[0]) / S.stepx) + 1; if (b > nx - 1) b = nx - 1; if (b < 0) b = 0;
+  while (b < nx - 1 && lin_at(S.b[0], S.b[1], S.stepx, nx, b + 1) <= x_max) ++b;
+  while (b >= 0 && !(lin_at(S.b[0], S.b[1], S.stepx, nx, b) <= x_max)) --b;
+  lo = a; hi = b;
+}
+
+// distance_checker.check (collision_check.py:144-240), warp-collective: all 32 lanes call it
+// with the same pose; returns the same bool on every lane.
+__device__ __forceinline__ bool check_distance_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
+                                                    const int32_t *col_start, double x, double y, double th) {
+  const int lane = threadIdx.x & 31;
+  VehGeom g;
+  veh_geom(c, x, y, th, g);
+  int lo, hi;
+  col_range(S, g.x_min, g.x_max, lo, hi);
+  if (lo > hi) return false;
+  const int beg = col_start[lo], end = col_start[hi + 1];
+  bool hit = false;
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    bool h = false;
+    if (i < end) {
+      const double2 p = cells[i];
+      if (p.x >= g.x_min && p.x <= g.x_max && p.y >= g.y_min && p.y <= g.y_max) h = cell_hits(g, p.x, p.y);
+    }
+    if (__any_sync(AVP_FULL_MASK, h)) { hit = true; break; }
+  }
+  return hit;
+}
+
+// two_circle_checker.check (collision_check.py:88-137), warp-collective
+__device__ __forceinline__ bool check_circle_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
+                                                  double x, double y, double th) {
+  const int lane = threadIdx.x & 31;
+  const double h2 = (c.lr + c.lw + c.lf) / 2;
+  const double Rd = 0.5 * sqrt(h2 * h2 + c.lb * c.lb);     // NOTE: x*x stands in for libm pow(x, 2)
+  const double cs = avp_cos(th), sn = avp_sin(th);
+  const double kf = 1.0 / 4 * (3 * c.lw + 3 * c.lf - c.lr), kr = 1.0 / 4 * (c.lw + c.lf - 3 * c.lr);
+  const double fx = x + kf * cs, fy = y + kf * sn, rx = x + kr * cs, ry = y + kr * sn;
+  double right, left, upper, down;
+  if (fx >= rx) { right = fx + Rd; left = rx - Rd; } else { right = rx + Rd; left = fx - Rd; }
+  if (fy >= ry) { upper = fy + Rd; down = ry - Rd; } else { upper = ry + Rd; down = fy - Rd; }
+  bool hit = false;
+  for (int base = 0; base < S.n_obs; base += 32) {
+    const int i = base + lane;
+    bool h = false;
+    if (i < S.n_obs) {
+      const double2 p = cells[i];
+      if (p.x > left && p.x < right && p.y > down && p.y < upper) {
+        const double ax = p.x - fx, ay = p.y - fy, bx = p.x - rx, by = p.y - ry;
+        h = (sqrt(ax * ax + ay * ay) <= Rd) || (sqrt(bx * bx + by * by) <= Rd);
+      }
+    }
+    if (__any_sync(AVP_FULL_MASK, h)) { hit = true; break; }
+  }
+  return hit;
+}
+
+__device__ __forceinline__ bool check_pose_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
+                                                const int32_t *col_start, double x, double y, double th) {
+  return c.collision_mode == 1 ? check_circle_warp(c, S, cells, x, y, th)
+                               : check_distance_warp(c, S, cells, col_start, x, y, th);
+}
+
+// ------------------------------------------------------------------------------------------
+// Reeds-Shepp (path_plan/rs_curve.py).  46 word instances, in the reference's order:
+//   0-1 SLS | 2-5 LSL | 6-9 LSR | 10-13 LRL | 14-17 LRL backwards | 18-21 LRLRn | 22-25 LRLRp |
+//   26-29 LRSL | 30-33 LRSR | 34-37 LRSL backwards | 38-41 LRSR backwards | 42-45 LRSLR
+#define RS_NINST 46
+
+// ctype ids (set_path compares ctypes lists for equality, rs_curve.py:144)
+enum { CT_SLS, CT_SRS, CT_LSL, CT_RSR, CT_LSR, CT_RSL, CT_LRL, CT_RLR, CT_LRLR, CT_RLRL, CT_LRSL, CT_RLSR,
+       CT_LRSR, CT_RLSL, CT_LSRL, CT_RSLR, CT_RSRL, CT_LSLR, CT_LRSLR, CT_RLSRL, CT_COUNT };
+
+__device__ __constant__ char rs_ct_names[CT_COUNT][8] = {
+  "SLS", "SRS", "LSL", "RSR", "LSR", "RSL", "LRL", "RLR", "LRLR", "RLRL", "LRSL", "RLSR",
+  "LRSR", "RLSL", "LSRL", "RSLR", "RSRL", "LSLR", "LRSLR", "RLSRL"};
+
+__device__ __forceinline__ void rs_R(double x, double y, double &r, double &th) { r = py_hypot(x, y); th = atan2(y, x); }
+
+// rs_curve.py:213-229
+__device__ __forceinline__ bool rs_SLS(double x, double y, double phi, double &t, double &u, double &v) {
+  phi = rs_M(phi);
+  if (y > 0.0 && 0.0 < phi && phi < AVP_PI * 0.99) {
+    const double tp = tan(phi), xd = -y / tp + x, th2 = tan(phi / 2.0);
+    const double dx = x - xd;
+    t = xd - th2; u = phi; v = sqrt(dx * dx + y * y) - th2;     // ** 2 : x*x stands in for libm pow
+    return true;
+  } else if (y < 0.0 && 0.0 < phi && phi < AVP_PI * 0.99) {
+    const double tp = tan(phi), xd = -y / tp + x, th2 = tan(phi / 2.0);
+    const double dx = x - xd;
+    t = xd - th2; u = phi; v = -sqrt(dx * dx + y * y) - th2;
+    return true;
+  }
+  return false;
+}
+// rs_curve.py:159-167
+__device__ __forceinline__ bool rs_LSL(double x, double y, double phi, double &t, double &u, double &v) {
+  double uu, tt; rs_R(x - avp_sin(phi), y - 1.0 + avp_cos(phi), uu, tt);
+  if (tt >= 0.0) { const double vv = rs_M(phi - tt); if (vv >= 0.0) { t = tt; u = uu; v = vv; return true; } }
+  return false;
+}
+// rs_curve.py:170-183
+__device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double &t, double &u, double &v) {
+  double u1, t1; rs_R(x + avp_sin(phi), y - 1.0 - avp_cos(phi), u1, t1);
+  u1 = u1 * u1;                                                    // u1 ** 2
+  if (u1 >= 4.0) {
+    const double uu = sqrt(u1 - 4.0), theta = atan2(2.0, uu), tt = rs_M(t1 + theta), vv = rs_M(tt - phi);
+    if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
+  }
+  return false;
+}
+// rs_curve.py:186-197
+__device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double &t, double &u, double &v) {
+  double u1, t1; rs_R(x - avp_sin(phi), y - 1.0 + avp_cos(phi), u1, t1);
+  if (u1 <= 4.0) {
+    const double uu = -2.0 * asin(0.25 * u1), tt = rs_M(t1 + 0.5 * uu + AVP_PI), vv = rs_M(phi - tt + uu);
+    if (tt >= 0.0 && uu <= 0.0) { t = tt; u = uu; v = vv; return true; }
+  }
+  return false;
+}
+// rs_curve.py:308-323
+__device__ __forceinline__ void rs_tauOmega(double u, double v, double xi, double eta, double phi, double &tau, double &omega) {
+  const double delta = rs_M(u - v), A = avp_sin(u) - avp_sin(delta), B = avp_cos(u) - avp_cos(delta) - 1.0;
+  const double t1 = atan2(eta * A - xi * B, xi * A + eta * B);
+  const double t2 = 2.0 * (avp_cos(delta) - avp_cos(v) - avp_cos(u)) + 3.0;
+  tau = (t2 < 0) ? rs_M(t1 + AVP_PI) : rs_M(t1);
+  omega = rs_M(tau - u + v - phi);
+}
+// rs_curve.py:326-337
+__device__ __forceinline__ bool rs_LRLRn(double x, double y, double phi, double &t, double &u, double &v) {
+  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi), rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
+  if (rho <= 1.0) {
+    const double uu = acos(rho); double tt, vv; rs_tauOmega(uu, -uu, xi, eta, phi, tt, vv);
+    if (tt >= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
+  }
+  return false;
+}
+// rs_curve.py:340-352
+__device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double &t, double &u, double &v) {
+  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi), rho = (20.0 - xi * xi - eta * eta) / 16.0;
+  if (0.0 <= rho && rho <= 1.0) {
+    const double uu = -acos(rho);
+    if (uu >= -0.5 * AVP_PI) {
+      double tt, vv; rs_tauOmega(uu, uu, xi, eta, phi, tt, vv);
+      if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
+    }
+  }
+  return false;
+}
+// rs_curve.py:391-403
+__device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double &t, double &u, double &v) {
+  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi); double rho, theta; rs_R(-eta, xi, rho, theta);
+  if (rho >= 2.0) {
+    const double tt = theta, uu = 2.0 - rho, vv = rs_M(tt + 0.5 * AVP_PI - phi);
+    if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
+  }
+  return false;
+}
+// rs_curve.py:406-419
+__device__ __forceinline__ bool rs_LRSL(double x, double y, double phi, double &t, double &u, double &v) {
+  const double xi = x - avp_sin(phi), eta = y - 1.0 + avp_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
+  if (rho >= 2.0) {
+    const double r = sqrt(rho * rho - 4.0), uu = 2.0 - r, tt = rs_M(theta + atan2(r, -2.0)), vv = rs_M(phi - 0.5 * AVP_PI - tt);
+    if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
+  }
+  return false;
+}
+// rs_curve.py:494-510
+__device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double &t, double &u, double &v) {
+  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
+  if (rho >= 2.0) {
+    const double uu = 4.0 - sqrt(rho * rho - 4.0);
+    if (uu <= 0.0) {
+      const double tt = rs_M(atan2((4.0 - uu) * xi - 2.0 * eta, -2.0 * xi + (uu - 4.0) * eta)), vv = rs_M(tt - phi);
+      if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
+    }
+  }
+  return false;
+}
+
+// normalised query of generate_path (rs_curve.py:627-634)
+struct RsQuery { double x, y, phi, xb, yb; };
+__device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
+  const double dx = q1[0] - q0[0], dy = q1[1] - q0[1], dth = q1[2] - q0[2];
+  const double c = avp_cos(q0[2]), s = avp_sin(q0[2]);
+  Q.x = (c * dx + s * dy) * maxc; Q.y = (-s * dx + c * dy) * maxc; Q.phi = dth;
+  const double cp = avp_cos(dth), sp = avp_sin(dth);
+  Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;          // rs_curve.py:286-287, :456-457
+}
+
+// one word instance -> (valid, t, u, v)
+__device__ __forceinline__ bool rs_eval_instance(int inst, const RsQuery &Q, double &t, double &u, double &v) {
+  if (inst < 2) return rs_SLS(Q.x, inst ? -Q.y : Q.y, inst ? -Q.phi : Q.phi, t, u, v);
+  const int r = (inst - 2) & 3, fam = (inst - 2) >> 2;   // fam 0 LSL,1 LSR,2 LRL,3 LRLb,4 LRLRn,5 LRLRp,6 LRSL,7 LRSR,8 LRSLb,9 LRSRb,10 LRSLR
+  const bool back = (fam == 3 || fam == 8 || fam == 9);
+  const double bx = back ? Q.xb : Q.x, by = back ? Q.yb : Q.y;
+  const double x = (r & 1) ? -bx : bx, y = (r & 2) ? -by : by, phi = (r == 1 || r == 2) ? -Q.phi : Q.phi;
+  switch (fam) {
+    case 0: return rs_LSL(x, y, phi, t, u, v);
+    case 1: return rs_LSR(x, y, phi, t, u, v);
+    case 2: case 3: return rs_LRL(x, y, phi, t, u, v);
+    case 4: return rs_LRLRn(x, y, phi, t, u, v);
+    case 5: return rs_LRLRp(x, y, phi, t, u, v);
+    case 6: case 8: return rs_LRSL(x, y, phi, t, u, v);
+    case 7: case 9: return rs_LRSR(x, y, phi, t, u, v);
+    default: return rs_LRSLR(x, y, phi, t, u, v);
+  }
+}
+
+// instance -> (ctype id, lengths[], n, np-type mask); arrangement per rs_curve.py:200-534
+__device__ __forceinline__ int rs_arrange(int inst, double t, double u, double v, int xy_np, int phi_np,
+                                          double *l, int &ct, unsigned &mask) {
+  const unsigned P = phi_np ? 1u : 0u;
+  if (inst < 2) { l[0] = t; l[1] = u; l[2] = v; ct = inst ? CT_SRS : CT_SLS; mask = (xy_np ? 1u : 0u) | (P << 1); return 3; }
+  const int r = (inst - 2) & 3, fam = (inst - 2) >> 2, hi = r >> 1;
+  const double s = (r & 1) ? -1.0 : 1.0;
+  switch (fam) {
+    case 0: l[0] = s * t; l[1] = s * u; l[2] = s * v; ct = hi ? CT_RSR : CT_LSL; mask = P << 2; return 3;
+    case 1: l[0] = s * t; l[1] = s * u; l[2] = s * v; ct = hi ? CT_RSL : CT_LSR; mask = P << 2; return 3;
+    case 2: l[0] = s * t; l[1] = s * u; l[2] = s * v; ct = hi ? CT_RLR : CT_LRL; mask = P << 2; return 3;
+    case 3: l[0] = s * v; l[1] = s * u; l[2] = s * t; ct = hi ? CT_RLR : CT_LRL; mask = P; return 3;
+    case 4: l[0] = s * t; l[1] = s * u; l[2] = s * -u; l[3] = s * v; ct = hi ? CT_RLRL : CT_LRLR; mask = P << 3; return 4;
+    case 5: l[0] = s * t; l[1] = s * u; l[2] = s * u; l[3] = s * v; ct = hi ? CT_RLRL : CT_LRLR; mask = P << 3; return 4;
+    case 6: l[0] = s * t; l[1] = s * -AVP_HALF_PI; l[2] = s * u; l[3] = s * v; ct = hi ? CT_RLSR : CT_LRSL; mask = P << 3; return 4;
+    case 7: l[0] = s * t; l[1] = s * -AVP_HALF_PI; l[2] = s * u; l[3] = s * v; ct = hi ? CT_RLSL : CT_LRSR; mask = P << 3; return 4;
+    case 8: l[0] = s * v; l[1] = s * u; l[2] = s * -AVP_HALF_PI; l[3] = s * t; ct = hi ? CT_RSLR : CT_LSRL; mask = P; return 4;
+    case 9: l[0] = s * v; l[1] = s * u; l[2] = s * -AVP_HALF_PI; l[3] = s * t; ct = hi ? CT_LSLR : CT_RSRL; mask = P; return 4;
+    default: l[0] = s * t; l[1] = s * -AVP_HALF_PI; l[2] = s * u; l[3] = s * -AVP_HALF_PI; l[4] = s * v; ct = hi ? CT_RLSRL : CT_LRSLR; mask = P << 4; return 5;
+  }
+}
+
+// Candidate results of the 46 instances (filled in parallel), then the sequential
+// set_path / calc_optimal_path semantics (rs_curve.py:137-156, :99-110).
+struct RsCand { double t, u, v; };
+
+struct RsBest { int ok; int degenerate; int n; int ct; double len[5]; double L; /* normalised */ };
+
+__device__ __forceinline__ int rs_group_start(int inst) {
+  // first instance that can share a ctype with `inst` (same family pair)
+  if (inst < 2) return inst;
+  const int fam = (inst - 2) >> 2;
+  const int gfam = (fam == 3) ? 2 : (fam == 5) ? 4 : fam;
+  return 2 + 4 * gfam;
+}
+
+__device__ __forceinline__ void rs_select(const RsCand *cand, unsigned long long valid, int xy_np, int phi_np,
+                                          double maxc, RsBest &best) {
+  unsigned long long retained = 0ull;
+  best.ok = 0; best.degenerate = 0;
+  double minL = 0.0; bool first = true;
+  for (int inst = 0; inst < RS_NINST; ++inst) {
+    if (!((valid >> inst) & 1ull)) continue;
+    double l[5]; int ct; unsigned mask;
+    const int n = rs_arrange(inst, cand[inst].t, cand[inst].u, cand[inst].v, xy_np, phi_np, l, ct, mask);
+    bool dup = false;
+    for (int e = rs_group_start(inst); e < inst; ++e) {
+      if (!((retained >> e) & 1ull)) continue;
+      double le[5], d[5]; int cte; unsigned me;
+      rs_arrange(e, cand[e].t, cand[e].u, cand[e].v, xy_np, phi_np, le, cte, me);
+      if (cte != ct) continue;
+      for (int i = 0; i < n; ++i) d[i] = le[i] - l[i];
+      if (py_sum(d, n, mask) <= 0.01) { dup = true; break; }     // rs_curve.py:143-146
+    }
+    if (dup) continue;
+    double a[5];
+    for (int i = 0; i < n; ++i) a[i] = fabs(l[i]);
+    const double L = py_sum(a, n, mask);                          // rs_curve.py:148
+    if (L >= 1000.0) continue;                                    // MAX_LENGTH
+    if (!(L >= 0.01)) { best.degenerate = 1; continue; }          // assert (rs_curve.py:153)
+    retained |= (1ull << inst);
+    const double Lm = L / maxc;
+    if (first || Lm <= minL) {           // last <= wins (rs_curve.py:106-108)
+      first = false; minL = Lm; best.ok = 1; best.n = n; best.ct = ct; best.L = L;
+      for (int i = 0; i < n; ++i) best.len[i] = l[i];
+    }
+  }
+}
+
+// rs_curve.py:597-624
+__device__ __forceinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
+                                               double &px, double &py, double &pyaw, int &dir) {
+  if (m == 'S') {
+    px = ox + l / maxc * avp_cos(oyaw); py = oy + l / maxc * avp_sin(oyaw); pyaw = oyaw;
+  } else {
+    const double ldx = avp_sin(l) / maxc;
+    double ldy = 0.0;
+    if (m == 'L') ldy = (1.0 - avp_cos(l)) / maxc; else if (m == 'R') ldy = (1.0 - avp_cos(l)) / (-maxc);
+    const double cm = avp_cos(-oyaw), sm = avp_sin(-oyaw);
+    const double gdx = cm * ldx + sm * ldy, gdy = -sm * ldx + cm * ldy;
+    px = ox + gdx; py = oy + gdy;
+  }
+  if (m == 'L') pyaw = oyaw + l; else if (m == 'R') pyaw = oyaw - l;
+  dir = (l > 0.0) ? 1 : -1;
+}
+
+// rs_curve.py:537-594 + the global transform of calc_all_paths (:124-130); single thread.
+// Returns the number of course points, or -1 on buffer overflow.
+__device__ __noinline__ int rs_course(const RsBest &w, double maxc, double step_size, const double q0[3], int cap,
+                                      double *X, double *Y, double *YAW, int32_t *DIR) {
+  const double step = step_size * maxc;
+  const int point_num = (int)(w.L / step) + w.n + 3;
+  if (point_num > cap) return -1;
+  for (int i = 0; i < point_num; ++i) { X[i] = 0.0; Y[i] = 0.0; YAW[i] = 0.0; DIR[i] = 0; }
+  const char *mode = rs_ct_names[w.ct];
+  int ind = 1;
+  DIR[0] = (w.len[0] > 0.0) ? 1 : -1;
+  double d = (w.len[0] > 0.0) ? step : -step, pd = d, ll = 0.0;
+  for (int i = 0; i < w.n; ++i) {
+    const char m = mode[i]; const double l = w.len[i];
+    d = (l > 0.0) ? step : -step;
+    const double ox = X[ind], oy = Y[ind], oyaw = YAW[ind];
+    ind -= 1;
+    if (i >= 1 && (w.len[i - 1] * w.len[i]) > 0) pd = -d - ll; else pd = d - ll;
+    while (fabs(pd) <= fabs(l)) {
+      ind += 1; if (ind >= point_num) return -1;
+      rs_interpolate(pd, m, maxc, ox, oy, oyaw, X[ind], Y[ind], YAW[ind], DIR[ind]);
+      pd += d;
+    }
+    ll = l - pd - d;
+    ind += 1; if (ind >= point_num) return -1;
+    rs_interpolate(l, m, maxc, ox, oy, oyaw, X[ind], Y[ind], YAW[ind], DIR[ind]);
+  }
+  int n = point_num;
+  while (n > 0 && X[n - 1] == 0.0) --n;
+  const double cm = avp_cos(-q0[2]), sm = avp_sin(-q0[2]);
+  for (int i = 0; i < n; ++i) {
+    const double ix = X[i], iy = Y[i];
+    X[i] = cm * ix + sm * iy + q0[0]; Y[i] = -sm * ix + cm * iy + q0[1];
+    YAW[i] = pi_2_pi(YAW[i] + q0[2]);
+  }
+  return n;
+}

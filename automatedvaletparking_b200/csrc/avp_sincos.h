@@ -33,11 +33,13 @@
 #define AVP_HD static inline
 #endif
 
+#if defined(__CUDACC__)
+__device__ static const double avp_sincos_tab_d[AVP_SINCOS_TAB_N] = {AVP_SINCOS_TAB_VALUES};
+#endif
 #if defined(__CUDA_ARCH__)
 #define AVP_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define AVP_ADD(a, b) __dadd_rn((a), (b))
 #define AVP_MUL(a, b) __dmul_rn((a), (b))
-__device__ static const double avp_sincos_tab_d[AVP_SINCOS_TAB_N] = {AVP_SINCOS_TAB_VALUES};
 #define AVP_SCT(i) (avp_sincos_tab_d[(i)])
 #else
 #define AVP_FMA(a, b, c) fma((a), (b), (c))

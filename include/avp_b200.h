@@ -117,7 +117,7 @@ int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, const int32_t
 int avp_rasterise(avp_ctx *ctx);
 
 /* replaces reading Map.cost_map / map_position / boundary / _discrete_x/_y of scenario s.
- * dims[2]=(nx,ny); geom[6]=(b0,b1,b2,b3,dx,dy); cost_map: nx*ny bytes (0/255) indexed [ix*ny+iy],
+ * dims[4]=(nx,ny,n_obs,raster_error); geom[6]=(b0,b1,b2,b3,dx,dy); cost_map: nx*ny bytes (0/255) indexed [ix*ny+iy],
  * may be NULL to query the sizes only. */
 int avp_fetch_map(avp_ctx *ctx, int s, int32_t *dims, double *geom, uint8_t *cost_map, int64_t cap);
 
@@ -134,8 +134,13 @@ int avp_expand_pure(avp_ctx *ctx, int s, const double parent_pose[3], double *ou
 
 /* replaces rs_curve.calc_optimal_path (rs_curve.py:99-134) for m (start, goal) pairs
  * (6 doubles each): selected word only.  lengths[m*5], ctypes[m*8], nseg[m], L[m];
- * course arrays (x, y, yaw: m*cap_pts doubles; dir: m*cap_pts int32) and n_pts[m]. */
-int avp_rs_optimal(avp_ctx *ctx, int m, const double *q, double maxc, double step_size,
+ * course arrays (x, y, yaw: m*cap_pts doubles; dir: m*cap_pts int32) and n_pts[m].
+ * nseg[i] = -1: no word; -2: degenerate (reference AssertionError, rs_curve.py:153).
+ * xy_np / phi_np: whether the reference call would see numpy scalars for the normalised
+ * (x, y) and for phi = gyaw - syaw.  CPython's sum() adds exact Python floats with Neumaier
+ * compensation but numpy scalars naively, so set_path's length sums (rs_curve.py:145,148)
+ * depend on it; on the planner path xy_np = 1 and phi_np = (node is not the root). */
+int avp_rs_optimal(avp_ctx *ctx, int m, const double *q, double maxc, double step_size, int xy_np, int phi_np,
                    double *lengths, char *ctypes, int32_t *nseg, double *L, int cap_pts,
                    double *x, double *y, double *yaw, int32_t *dir, int32_t *n_pts);
 
@@ -153,9 +158,16 @@ int avp_plan_batch_resident(avp_ctx *ctx, float *elapsed_ms);
 /* copy results of the last avp_plan_batch_resident to host buffers (same layout as above) */
 int avp_fetch_results(avp_ctx *ctx, avp_plan_summary *summaries, double *final_path, int cap_path,
                       int32_t *pops, int cap_pops);
-/* device pointer + byte size of the packed per-scenario result records (for the NCCL
- * all-gather of finished trajectories) */
-int avp_result_device_buffer(avp_ctx *ctx, void **dptr, int64_t *bytes, int64_t *stride);
+/* allocate result buffers for the resident leg: cap_path rows per scenario, cap_pops pop slots */
+int avp_plan_configure(avp_ctx *ctx, int cap_path, int cap_pops);
+/* device pointers of the per-scenario result records (summaries: n * sizeof(avp_plan_summary);
+ * paths: n * cap_path * 3 doubles) for the NCCL all-gather of finished trajectories */
+int avp_result_device_buffer(avp_ctx *ctx, void **sums, void **paths, int64_t *n, int64_t *cap_path);
+/* the first <= 256 Dijkstra.compute_path calls of scenario s: (terminate grid id, returned
+ * distance, len(closedlist) afterwards) triples -- the observable trace of compute_h.py:198-214 */
+int avp_fetch_hq_log(avp_ctx *ctx, int s, int32_t *log3, int cap_entries);
+/* SM count, persistent-grid size (CTAs) and CTA width of the search kernel */
+int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block);
 
 /* per-scenario h-table readback: replaces iterating Dijkstra.closedlist (compute_h.py:80):
  * hval[id] = distance of the first closedlist entry with grid_id == id, -1 if none. */
