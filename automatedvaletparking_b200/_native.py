@@ -22,7 +22,7 @@ EXPORTS = [
     "avp_create", "avp_destroy", "avp_last_error", "avp_launch_count", "avp_scenarios_upload", "avp_rasterise",
     "avp_fetch_map", "avp_collision_check", "avp_expand_pure", "avp_rs_optimal", "avp_plan_batch",
     "avp_plan_batch_resident", "avp_fetch_results", "avp_plan_configure", "avp_result_device_buffer",
-    "avp_fetch_hvalues", "avp_fetch_hq_log", "avp_device_info",
+    "avp_fetch_hvalues", "avp_fetch_hq_log", "avp_device_info", "avp_set_watchdog", "avp_fetch_debug",
 ]
 
 _lib = None
@@ -64,6 +64,8 @@ def lib():
     L.avp_fetch_hvalues.argtypes = [c_vp, ctypes.c_int, c_ip, ctypes.c_int64, c_lp]
     L.avp_fetch_hq_log.argtypes = [c_vp, ctypes.c_int, c_ip, ctypes.c_int]
     L.avp_device_info.argtypes = [c_vp, c_ip, c_ip, c_ip]
+    L.avp_set_watchdog.argtypes = [c_vp, ctypes.c_longlong]
+    L.avp_fetch_debug.argtypes = [c_vp, c_ip]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = the header and the library disagree
     _lib = L

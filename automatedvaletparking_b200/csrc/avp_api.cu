@@ -7,6 +7,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <time.h>
 #include "avp_kernels.cuh"
 
 struct avp_ctx {
@@ -35,7 +36,7 @@ struct avp_ctx {
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
-  int *d_counter = nullptr;
+  int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // scratch for the small API kernels
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -85,7 +86,7 @@ static void free_scenarios(avp_ctx *ctx) {
   ctx->n = 0; ctx->rasterised = false;
 }
 static void free_results(avp_ctx *ctx) {
-  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq);
+  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq); free_dev(ctx->d_dbg); ctx->d_dbg = nullptr;
   ctx->d_sums = nullptr; ctx->d_paths = nullptr; ctx->d_pops = nullptr; ctx->d_hq = nullptr; ctx->res_n = 0;
 }
 static void free_ws(avp_ctx *ctx) {
@@ -298,6 +299,8 @@ static int ensure_results(avp_ctx *ctx, int cap_path, int cap_pops) {
   CK(cudaMalloc(&ctx->d_paths, sizeof(double) * n * cap_path * 3));
   CK(cudaMalloc(&ctx->d_pops, sizeof(int32_t) * n * (size_t)(cap_pops > 0 ? cap_pops : 1)));
   CK(cudaMalloc(&ctx->d_hq, sizeof(int32_t) * n * AVP_HQ_CAP * 3));
+  CK(cudaMalloc(&ctx->d_dbg, sizeof(int) * n * 8));
+  CK(cudaMemset(ctx->d_dbg, 0, sizeof(int) * n * 8));
   ctx->res_n = ctx->n; ctx->cap_path = cap_path; ctx->cap_pops = cap_pops;
   return 0;
 }
@@ -314,13 +317,33 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
-  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter;
+  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.watchdog_cycles = ctx->watchdog_cycles;
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   k_search<<<grid, AVP_BLOCK, 0, ctx->stream>>>(P); ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());
+  const char *lim = getenv("AVP_HOST_TIMEOUT_S");        // development aid: never wait forever on a kernel
+  if (lim && atof(lim) > 0) {
+    const double limit = atof(lim);
+    timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (;;) {
+      cudaError_t q = cudaEventQuery(ctx->ev1);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) { ctx->err = std::string("k_search: ") + cudaGetErrorString(q); return -1; }
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > limit) {
+        std::vector<int> dbg((size_t)ctx->n * 8, 0);
+        cudaMemcpy(dbg.data(), ctx->d_dbg, sizeof(int) * dbg.size(), cudaMemcpyDeviceToHost);
+        std::string msg = "k_search timed out; per-scenario (phase,pops,h_closed,open):";
+        for (int i = 0; i < ctx->n && i < 64; ++i) { char b[96]; snprintf(b, sizeof b, " [%d: %d,%d,%d,%d]", i, dbg[8 * i], dbg[8 * i + 1], dbg[8 * i + 2], dbg[8 * i + 3]); msg += b; }
+        ctx->err = msg;
+        return -11;
+      }
+      timespec ts = {0, 2000000}; nanosleep(&ts, nullptr);
+    }
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
   return 0;
@@ -396,5 +419,15 @@ extern "C" int avp_fetch_hq_log(avp_ctx *ctx, int s, int32_t *log3, int cap_entr
 extern "C" int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block) {
   if (!ctx) return -3;
   if (n_sm) *n_sm = ctx->n_sm; if (slots) *slots = ctx->slots; if (block) *block = AVP_BLOCK;
+  return 0;
+}
+
+/* development aids: per-scenario progress checkpoints and an in-kernel watchdog (SM clock cycles) */
+extern "C" int avp_set_watchdog(avp_ctx *ctx, long long cycles) { if (!ctx) return -3; ctx->watchdog_cycles = cycles; return 0; }
+extern "C" int avp_fetch_debug(avp_ctx *ctx, int32_t *out8n) {
+  if (!ctx) return -3;
+  if (!ctx->d_dbg) FAIL("avp_fetch_debug: no results");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(out8n, ctx->d_dbg, sizeof(int) * (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
   return 0;
 }

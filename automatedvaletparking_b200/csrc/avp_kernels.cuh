@@ -55,6 +55,8 @@ struct KParams {
   int32_t *pops; int cap_pops;
   int32_t *hq_log;                // n * AVP_HQ_CAP * 3, may be NULL
   int *work_counter;
+  int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
+  long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY
 };
 
 // ------------------------------------------------------------------------------------------
@@ -317,7 +319,8 @@ __device__ __noinline__ int dij_compute_path(DijCtx &D, double node_x, double no
   const long long gid = map_index(S, cur_x, cur_y);
   if (lane == 0) { D.closed_len++; if (gid >= 0 && gid < S.n_ids && D.hval[gid] < 0) D.hval[gid] = 0; }   // initial_map (:50-72)
   __syncwarp();
-  for (;;) {
+  for (long long guard = 0;; ++guard) {
+    if (guard > 4ll * S.n_ids + 1024) { if (lane == 0) D.status = AVP_CAPACITY; __syncwarp(); return -1; }   // cannot happen: every id is pushed at most twice
     // update_openlist (compute_h.py:84-195): the 8 neighbours evaluated by lanes 0..7
     bool valid = false; int prio = 0, st = 0; long long nid = 0; double ngx = 0.0, ngy = 0.0;
     if (lane < 8) {
@@ -396,16 +399,19 @@ __device__ __forceinline__ unsigned long long pose_hash(double x, double y, doub
 }
 // exact-pose lookup: replaces the == scans over closed_list / open_list.queue (hybrid_a_star.py:155-172)
 __device__ __forceinline__ int htab_find(const int32_t *htab, int mask, const Node *nodes, double x, double y, double t) {
-  for (unsigned long long p = pose_hash(x, y, t);; ++p) {
+  unsigned long long p = pose_hash(x, y, t);
+  for (int probes = 0; probes <= mask; ++probes, ++p) {
     const int e = htab[p & mask];
     if (e < 0) return -1;
     const Node &n = nodes[e];
     if (n.x == x && n.y == y && n.theta == t) return e;
   }
+  return -1;
 }
 __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node *nodes, int idx) {
   const Node &n = nodes[idx];
-  for (unsigned long long p = pose_hash(n.x, n.y, n.theta);; ++p) if (htab[p & mask] < 0) { htab[p & mask] = idx; return; }
+  unsigned long long p = pose_hash(n.x, n.y, n.theta);
+  for (int probes = 0; probes <= mask; ++probes, ++p) if (htab[p & mask] < 0) { htab[p & mask] = idx; return; }
 }
 // open_list: heapq of node indices ordered by Node.__lt__ (f only, hybrid_a_star.py:61-68)
 __device__ __forceinline__ void open_siftdown(int32_t *heap, const Node *nodes, int start, int pos) {
@@ -479,6 +485,9 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
     const double goal[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
     int32_t *pops = P.pops ? P.pops + (size_t)sc * P.cap_pops : nullptr;
     int32_t *hql = P.hq_log ? P.hq_log + (size_t)sc * AVP_HQ_CAP * 3 : nullptr;
+    int *dbg = P.dbg ? P.dbg + (size_t)sc * 8 : nullptr;
+    const long long t_start = clock64();
+    if (dbg && tid == 0) { dbg[0] = 1; dbg[1] = 0; }
 
     // ---- per-scenario initialisation (all threads)
     for (int i = tid; i < S.n_ids; i += AVP_BLOCK) { hval[i] = -1; ost[i] = -1; }
@@ -512,9 +521,12 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
 
     // ---- main loop (path_planner.py:68-98)
     bool reached = false;
+    if (dbg && tid == 0) dbg[0] = 2;
     for (;;) {
       __syncthreads();
       if (tid == 0) {
+        if (dbg) { dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_on; }
+        if (P.watchdog_cycles > 0 && clock64() - t_start > P.watchdog_cycles && s_status == 0) s_status = AVP_CAPACITY;
         if (s_status != 0 || s_on == 0) s_ctl = CTL_EXIT;
         else if (s_npops >= cfg.max_pops) { s_status = AVP_CAPACITY; s_ctl = CTL_EXIT; }
         else {
@@ -535,6 +547,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
       }
       __syncthreads();
       if (s_ctl == CTL_EXIT) break;
+      if (dbg && tid == 0) dbg[0] = 3;
       const int cur = s_cur;
       const Node cn = nodes[cur];
       const int phi_np = cur != 0;           // root theta is a Python float (see oracle generate_path)
@@ -563,6 +576,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
       }
       __syncthreads();
 
+      if (dbg && tid == 0) dbg[0] = 4;
       // phase 2: thread 0 selects the shot word and lays out its course; meanwhile the other
       // lanes/warps collision-check the sub-steps of new successors (hybrid_a_star.py:185-204)
       if (tid == 0 && s_in_radius) {
@@ -597,16 +611,20 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
       __syncthreads();
       if (s_shot_bad) { if (tid == 0) s_status = (s_shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; continue; }
 
+      if (dbg && tid == 0) dbg[0] = 5;
       // phase 3: collision check of the shot's course (hybrid_a_star.py:334-347)
       if (s_in_radius) {
-        for (int i = warp; i < s_npts; i += AVP_NWARPS) {
-          if (s_shot_coll) break;
+        const int npts = s_npts;
+        for (int i = warp; i < npts; i += AVP_NWARPS) {
+          const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
+          if (stop) break;
           if (check_pose_warp(cfg, S, cells, col_start, CX[i], CY[i], pi_2_pi(CYAW[i]))) { if (lane == 0) s_shot_coll = 1; }
         }
       }
       __syncthreads();
       if (s_in_radius && !s_shot_coll) { reached = true; break; }     // path_planner.py:86-88
 
+      if (dbg && tid == 0) dbg[0] = 6;
       // phase 4: rs lengths of the successors that will be scored (hybrid_a_star.py:286-294)
       for (int i = tid; i < nchild; i += AVP_BLOCK) {
         const int f = s_found[i];
@@ -630,6 +648,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
       }
       __syncthreads();
 
+      if (dbg && tid == 0) dbg[0] = 7;
       // phase 5: sequential commit in slot order by warp 0 (hybrid_a_star.py:154-239)
       if (warp == 0) {
         for (int i = 0; i < nchild; ++i) {
@@ -702,6 +721,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
     }
     __syncthreads();
 
+    if (dbg && tid == 0) dbg[0] = 8;
     // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
     if (tid == 0) {
       avp_plan_summary &R = P.sums[sc];
@@ -735,6 +755,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
         }
         R.n_astar = np_;
         for (int i = 1; i < s_npts; ++i) push(CX[i], CY[i], CYAW[i]);
+        if (dbg) dbg[0] = 9;
         R.n_final = np_; R.n_rs = s_npts; R.rs_nseg = s_best.n; R.rs_L = s_best.L / maxc;
         for (int i = 0; i < s_best.n; ++i) R.rs_lengths[i] = s_best.len[i] / maxc;
         for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = rs_ct_names[s_best.ct][i];

@@ -173,6 +173,13 @@ int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block)
  * hval[id] = distance of the first closedlist entry with grid_id == id, -1 if none. */
 int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *n_ids);
 
+/* development aids: an in-kernel watchdog (SM clock cycles per scenario, 0 = off; a scenario
+ * that exceeds it ends with AVP_CAPACITY) and the per-scenario progress checkpoints
+ * (8 int32 each: phase, pops, len(closedlist), open size, ...).  The environment variable
+ * AVP_HOST_TIMEOUT_S bounds the host's wait for the search kernel. */
+int avp_set_watchdog(avp_ctx *ctx, long long cycles);
+int avp_fetch_debug(avp_ctx *ctx, int32_t *out8n);
+
 #ifdef __cplusplus
 }
 #endif
