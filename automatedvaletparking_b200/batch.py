@@ -46,6 +46,16 @@ class PlanResults:
         return int(self.summaries["global_index"].astype(np.int64).sum())
 
 
+def _pi_2_pi(theta: float) -> float:
+    """rs_curve.pi_2_pi (rs_curve.py:649-656)"""
+    import math
+    while theta > math.pi:
+        theta -= 2.0 * math.pi
+    while theta < -math.pi:
+        theta += 2.0 * math.pi
+    return theta
+
+
 def _dp(a):
     return a.ctypes.data_as(_native.c_dp)
 
@@ -126,6 +136,18 @@ class DevicePlanner:
                  "avp_collision_check")
         return out.astype(bool)
 
+    def start_goal_collisions(self):
+        """distance_checker.check at every loaded scenario's start and goal pose (scenario recipes)."""
+        from . import hostcfg  # noqa: F401
+        a = np.zeros(self.n, dtype=bool)
+        b = np.zeros(self.n, dtype=bool)
+        P = self.batch.poses
+        for k in range(self.n):
+            # the search wraps headings with pi_2_pi (hybrid_a_star.py:105,109); check() sees the same values
+            r = self.check(k, [[P[k, 0], P[k, 1], _pi_2_pi(P[k, 2])], [P[k, 3], P[k, 4], _pi_2_pi(P[k, 5])]])
+            a[k], b[k] = r[0], r[1]
+        return a, b
+
     def expand_pure(self, s: int, parent):
         n = 2 * self.cfg.steering_angle_num
         p = np.array(parent, dtype=np.float64)
@@ -196,6 +218,25 @@ class DevicePlanner:
         out = np.zeros((256, 3), dtype=np.int32)
         self._ck(self._L.avp_fetch_hq_log(self._h, s, _ip(out), 256), "avp_fetch_hq_log")
         return out[:min(n_hq, 256)]
+
+    def rasterise(self):
+        self._ck(self._L.avp_rasterise(self._h), "avp_rasterise")
+
+    def timer_start(self):
+        self._ck(self._L.avp_timer_start(self._h), "avp_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float()
+        self._ck(self._L.avp_timer_stop(self._h, ctypes.byref(ms)), "avp_timer_stop")
+        return float(ms.value)
+
+    def last_search_ms(self) -> float:
+        ms = ctypes.c_float()
+        self._ck(self._L.avp_last_search_ms(self._h, ctypes.byref(ms)), "avp_last_search_ms")
+        return float(ms.value)
+
+    def set_watchdog(self, cycles: int):
+        self._ck(self._L.avp_set_watchdog(self._h, int(cycles)), "avp_set_watchdog")
 
     @property
     def launches(self) -> int:

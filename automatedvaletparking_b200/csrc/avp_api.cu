@@ -37,7 +37,7 @@ struct avp_ctx {
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
   int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
   // scratch for the small API kernels
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
 };
@@ -101,6 +101,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
   free_dev(ctx->d_counter); free_dev(ctx->d_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->evA) cudaEventDestroy(ctx->evA); if (ctx->evB) cudaEventDestroy(ctx->evB);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -429,5 +430,32 @@ extern "C" int avp_fetch_debug(avp_ctx *ctx, int32_t *out8n) {
   if (!ctx->d_dbg) FAIL("avp_fetch_debug: no results");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpy(out8n, ctx->d_dbg, sizeof(int) * (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* CUDA-event bracket on the context's stream, so callers can time any sequence of entry points
+ * (bench.py: resident step = rasterise + search; e2e step = upload + rasterise + search + fetch) */
+extern "C" int avp_timer_start(avp_ctx *ctx) {
+  if (!ctx) return -3;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->evA) { CK(cudaEventCreate(&ctx->evA)); CK(cudaEventCreate(&ctx->evB)); }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventRecord(ctx->evA, ctx->stream));
+  return 0;
+}
+extern "C" int avp_timer_stop(avp_ctx *ctx, float *elapsed_ms) {
+  if (!ctx) return -3;
+  if (!ctx->evA) FAIL("avp_timer_stop: timer not started");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->evB, ctx->stream));
+  CK(cudaEventSynchronize(ctx->evB));
+  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, ctx->evA, ctx->evB));
+  return 0;
+}
+/* CUDA-event duration of the most recent search kernel launch */
+extern "C" int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms) {
+  if (!ctx) return -3;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
   return 0;
 }

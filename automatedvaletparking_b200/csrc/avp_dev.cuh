@@ -8,7 +8,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/avp_b200.h"
-#include "avp_sincos.h"
+#include "avp_libm.h"
 
 #define AVP_PI 3.141592653589793  /* math.pi (rs_curve.py:25) */
 #define AVP_HALF_PI (0.5 * AVP_PI)
@@ -38,6 +38,16 @@ struct ScenDev {
 
 // ------------------------------------------------------------------------------------------
 // small math helpers
+
+// Out-of-line device entry points of the bit-exact libm restatements (avp_sincos.h, avp_libm.h):
+// one copy of each body per kernel keeps code size and register pressure down.
+__device__ __noinline__ double d_sin(double x) { return avp_sin(x); }
+__device__ __noinline__ double d_cos(double x) { return avp_cos(x); }
+__device__ __noinline__ double d_atan2(double y, double x) { return avp_atan2(y, x); }
+__device__ __noinline__ double d_asin(double x) { return avp_asin(x); }
+__device__ __noinline__ double d_acos(double x) { return avp_acos(x); }
+__device__ __noinline__ double d_tan(double x) { return avp_tan(x); }
+__device__ __noinline__ double d_pow2(double x) { return avp_pow2(x); }   // libm pow(x, 2.0)
 
 __device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double d_mul(double a, double b) { return __dmul_rn(a, b); }
@@ -132,7 +142,7 @@ struct VehGeom {
 };
 
 __device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y, double th, VehGeom &g) {
-  const double cs = avp_cos(th), sn = avp_sin(th);
+  const double cs = d_cos(th), sn = d_sin(th);
   const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
   const double lx0 = -c.lr - fr, lx1 = c.lw + c.lf + fr, ly0 = -c.lb / 2 - sd, ly1 = c.lb / 2 + sd;
   const double locx[4] = {lx0, lx1, lx1, lx0}, locy[4] = {ly0, ly0, ly1, ly1};
@@ -229,8 +239,8 @@ __device__ __forceinline__ bool check_circle_warp(const avp_config &c, const Sce
                                                   double x, double y, double th) {
   const int lane = threadIdx.x & 31;
   const double h2 = (c.lr + c.lw + c.lf) / 2;
-  const double Rd = 0.5 * sqrt(h2 * h2 + c.lb * c.lb);     // NOTE: x*x stands in for libm pow(x, 2)
-  const double cs = avp_cos(th), sn = avp_sin(th);
+  const double Rd = 0.5 * sqrt(d_pow2(h2) + d_pow2(c.lb));
+  const double cs = d_cos(th), sn = d_sin(th);
   const double kf = 1.0 / 4 * (3 * c.lw + 3 * c.lf - c.lr), kr = 1.0 / 4 * (c.lw + c.lf - 3 * c.lr);
   const double fx = x + kf * cs, fy = y + kf * sn, rx = x + kr * cs, ry = y + kr * sn;
   double right, left, upper, down;
@@ -243,8 +253,7 @@ __device__ __forceinline__ bool check_circle_warp(const avp_config &c, const Sce
     if (i < S.n_obs) {
       const double2 p = cells[i];
       if (p.x > left && p.x < right && p.y > down && p.y < upper) {
-        const double ax = p.x - fx, ay = p.y - fy, bx = p.x - rx, by = p.y - ry;
-        h = (sqrt(ax * ax + ay * ay) <= Rd) || (sqrt(bx * bx + by * by) <= Rd);
+        h = (sqrt(d_pow2(p.x - fx) + d_pow2(p.y - fy)) <= Rd) || (sqrt(d_pow2(p.x - rx) + d_pow2(p.y - ry)) <= Rd);
       }
     }
     if (__any_sync(AVP_FULL_MASK, h)) { hit = true; break; }
@@ -272,71 +281,69 @@ __device__ __constant__ char rs_ct_names[CT_COUNT][8] = {
   "SLS", "SRS", "LSL", "RSR", "LSR", "RSL", "LRL", "RLR", "LRLR", "RLRL", "LRSL", "RLSR",
   "LRSR", "RLSL", "LSRL", "RSLR", "RSRL", "LSLR", "LRSLR", "RLSRL"};
 
-__device__ __forceinline__ void rs_R(double x, double y, double &r, double &th) { r = py_hypot(x, y); th = atan2(y, x); }
+__device__ __forceinline__ void rs_R(double x, double y, double &r, double &th) { r = py_hypot(x, y); th = d_atan2(y, x); }
 
 // rs_curve.py:213-229
 __device__ __forceinline__ bool rs_SLS(double x, double y, double phi, double &t, double &u, double &v) {
   phi = rs_M(phi);
   if (y > 0.0 && 0.0 < phi && phi < AVP_PI * 0.99) {
-    const double tp = tan(phi), xd = -y / tp + x, th2 = tan(phi / 2.0);
-    const double dx = x - xd;
-    t = xd - th2; u = phi; v = sqrt(dx * dx + y * y) - th2;     // ** 2 : x*x stands in for libm pow
+    const double tp = d_tan(phi), xd = -y / tp + x, th2 = d_tan(phi / 2.0);
+    t = xd - th2; u = phi; v = sqrt(d_pow2(x - xd) + d_pow2(y)) - th2;     // ** 2 == libm pow(., 2.0)
     return true;
   } else if (y < 0.0 && 0.0 < phi && phi < AVP_PI * 0.99) {
-    const double tp = tan(phi), xd = -y / tp + x, th2 = tan(phi / 2.0);
-    const double dx = x - xd;
-    t = xd - th2; u = phi; v = -sqrt(dx * dx + y * y) - th2;
+    const double tp = d_tan(phi), xd = -y / tp + x, th2 = d_tan(phi / 2.0);
+    t = xd - th2; u = phi; v = -sqrt(d_pow2(x - xd) + d_pow2(y)) - th2;
     return true;
   }
   return false;
 }
 // rs_curve.py:159-167
 __device__ __forceinline__ bool rs_LSL(double x, double y, double phi, double &t, double &u, double &v) {
-  double uu, tt; rs_R(x - avp_sin(phi), y - 1.0 + avp_cos(phi), uu, tt);
+  double uu, tt; rs_R(x - d_sin(phi), y - 1.0 + d_cos(phi), uu, tt);
   if (tt >= 0.0) { const double vv = rs_M(phi - tt); if (vv >= 0.0) { t = tt; u = uu; v = vv; return true; } }
   return false;
 }
 // rs_curve.py:170-183
 __device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double &t, double &u, double &v) {
-  double u1, t1; rs_R(x + avp_sin(phi), y - 1.0 - avp_cos(phi), u1, t1);
-  u1 = u1 * u1;                                                    // u1 ** 2
+  double u1, t1; rs_R(x + d_sin(phi), y - 1.0 - d_cos(phi), u1, t1);
+  u1 = d_pow2(u1);                                                 // u1 ** 2 == libm pow(u1, 2.0)
   if (u1 >= 4.0) {
-    const double uu = sqrt(u1 - 4.0), theta = atan2(2.0, uu), tt = rs_M(t1 + theta), vv = rs_M(tt - phi);
+    const double uu = sqrt(u1 - 4.0), theta = d_atan2(2.0, uu), tt = rs_M(t1 + theta), vv = rs_M(tt - phi);
     if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
   return false;
 }
 // rs_curve.py:186-197
 __device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double &t, double &u, double &v) {
-  double u1, t1; rs_R(x - avp_sin(phi), y - 1.0 + avp_cos(phi), u1, t1);
+  double u1, t1; rs_R(x - d_sin(phi), y - 1.0 + d_cos(phi), u1, t1);
   if (u1 <= 4.0) {
-    const double uu = -2.0 * asin(0.25 * u1), tt = rs_M(t1 + 0.5 * uu + AVP_PI), vv = rs_M(phi - tt + uu);
+    const double uu = -2.0 * d_asin(0.25 * u1), tt = rs_M(t1 + 0.5 * uu + AVP_PI), vv = rs_M(phi - tt + uu);
     if (tt >= 0.0 && uu <= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
   return false;
 }
 // rs_curve.py:308-323
 __device__ __forceinline__ void rs_tauOmega(double u, double v, double xi, double eta, double phi, double &tau, double &omega) {
-  const double delta = rs_M(u - v), A = avp_sin(u) - avp_sin(delta), B = avp_cos(u) - avp_cos(delta) - 1.0;
-  const double t1 = atan2(eta * A - xi * B, xi * A + eta * B);
-  const double t2 = 2.0 * (avp_cos(delta) - avp_cos(v) - avp_cos(u)) + 3.0;
+  const double delta = rs_M(u - v), A = d_sin(u) - d_sin(delta), B = d_cos(u) - d_cos(delta) - 1.0;
+  const double t1 = d_atan2(eta * A - xi * B, xi * A + eta * B);
+  const double t2 = 2.0 * (d_cos(delta) - d_cos(v) - d_cos(u)) + 3.0;
   tau = (t2 < 0) ? rs_M(t1 + AVP_PI) : rs_M(t1);
   omega = rs_M(tau - u + v - phi);
 }
 // rs_curve.py:326-337
 __device__ __forceinline__ bool rs_LRLRn(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi), rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
+  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi), rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
   if (rho <= 1.0) {
-    const double uu = acos(rho); double tt, vv; rs_tauOmega(uu, -uu, xi, eta, phi, tt, vv);
+    const double uu = d_acos(rho); double tt, vv; rs_tauOmega(uu, -uu, xi, eta, phi, tt, vv);
     if (tt >= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
   return false;
 }
 // rs_curve.py:340-352
 __device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi), rho = (20.0 - xi * xi - eta * eta) / 16.0;
+  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi), rho = (20.0 - xi * xi - eta * eta) / 16.0;
   if (0.0 <= rho && rho <= 1.0) {
-    const double uu = -acos(rho);
+    const double uu = -d_acos(rho);
     if (uu >= -0.5 * AVP_PI) {
       double tt, vv; rs_tauOmega(uu, uu, xi, eta, phi, tt, vv);
       if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
@@ -346,7 +353,7 @@ __device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double 
 }
 // rs_curve.py:391-403
 __device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi); double rho, theta; rs_R(-eta, xi, rho, theta);
+  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi); double rho, theta; rs_R(-eta, xi, rho, theta);
   if (rho >= 2.0) {
     const double tt = theta, uu = 2.0 - rho, vv = rs_M(tt + 0.5 * AVP_PI - phi);
     if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
@@ -355,20 +362,20 @@ __device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double &
 }
 // rs_curve.py:406-419
 __device__ __forceinline__ bool rs_LRSL(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x - avp_sin(phi), eta = y - 1.0 + avp_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
+  const double xi = x - d_sin(phi), eta = y - 1.0 + d_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
   if (rho >= 2.0) {
-    const double r = sqrt(rho * rho - 4.0), uu = 2.0 - r, tt = rs_M(theta + atan2(r, -2.0)), vv = rs_M(phi - 0.5 * AVP_PI - tt);
+    const double r = sqrt(rho * rho - 4.0), uu = 2.0 - r, tt = rs_M(theta + d_atan2(r, -2.0)), vv = rs_M(phi - 0.5 * AVP_PI - tt);
     if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
   return false;
 }
 // rs_curve.py:494-510
 __device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + avp_sin(phi), eta = y - 1.0 - avp_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
+  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
   if (rho >= 2.0) {
     const double uu = 4.0 - sqrt(rho * rho - 4.0);
     if (uu <= 0.0) {
-      const double tt = rs_M(atan2((4.0 - uu) * xi - 2.0 * eta, -2.0 * xi + (uu - 4.0) * eta)), vv = rs_M(tt - phi);
+      const double tt = rs_M(d_atan2((4.0 - uu) * xi - 2.0 * eta, -2.0 * xi + (uu - 4.0) * eta)), vv = rs_M(tt - phi);
       if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
     }
   }
@@ -379,9 +386,9 @@ __device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double 
 struct RsQuery { double x, y, phi, xb, yb; };
 __device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
   const double dx = q1[0] - q0[0], dy = q1[1] - q0[1], dth = q1[2] - q0[2];
-  const double c = avp_cos(q0[2]), s = avp_sin(q0[2]);
+  const double c = d_cos(q0[2]), s = d_sin(q0[2]);
   Q.x = (c * dx + s * dy) * maxc; Q.y = (-s * dx + c * dy) * maxc; Q.phi = dth;
-  const double cp = avp_cos(dth), sp = avp_sin(dth);
+  const double cp = d_cos(dth), sp = d_sin(dth);
   Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;          // rs_curve.py:286-287, :456-457
 }
 
@@ -477,12 +484,12 @@ __device__ __forceinline__ void rs_select(const RsCand *cand, unsigned long long
 __device__ __forceinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
                                                double &px, double &py, double &pyaw, int &dir) {
   if (m == 'S') {
-    px = ox + l / maxc * avp_cos(oyaw); py = oy + l / maxc * avp_sin(oyaw); pyaw = oyaw;
+    px = ox + l / maxc * d_cos(oyaw); py = oy + l / maxc * d_sin(oyaw); pyaw = oyaw;
   } else {
-    const double ldx = avp_sin(l) / maxc;
+    const double ldx = d_sin(l) / maxc;
     double ldy = 0.0;
-    if (m == 'L') ldy = (1.0 - avp_cos(l)) / maxc; else if (m == 'R') ldy = (1.0 - avp_cos(l)) / (-maxc);
-    const double cm = avp_cos(-oyaw), sm = avp_sin(-oyaw);
+    if (m == 'L') ldy = (1.0 - d_cos(l)) / maxc; else if (m == 'R') ldy = (1.0 - d_cos(l)) / (-maxc);
+    const double cm = d_cos(-oyaw), sm = d_sin(-oyaw);
     const double gdx = cm * ldx + sm * ldy, gdy = -sm * ldx + cm * ldy;
     px = ox + gdx; py = oy + gdy;
   }
@@ -519,7 +526,7 @@ __device__ __noinline__ int rs_course(const RsBest &w, double maxc, double step_
   }
   int n = point_num;
   while (n > 0 && X[n - 1] == 0.0) --n;
-  const double cm = avp_cos(-q0[2]), sm = avp_sin(-q0[2]);
+  const double cm = d_cos(-q0[2]), sm = d_sin(-q0[2]);
   for (int i = 0; i < n; ++i) {
     const double ix = X[i], iy = Y[i];
     X[i] = cm * ix + sm * iy + q0[0]; Y[i] = -sm * ix + cm * iy + q0[1];

@@ -97,13 +97,13 @@ __global__ void k_raster(int n_scen, ScenDev *scen, const int32_t *nv, const int
     for (int i = 0; i < n0; ++i)
       if (n == 0 || px[i] != px[n - 1] || py[i] != py[n - 1]) { px[n] = px[i]; py[n] = py[i]; ++n; }
     const double cx = np_sum_dev(px, n) / n, cy = np_sum_dev(py, n) / n;           // :210-211
-    for (int i = 0; i < n; ++i) { ang[i] = atan2(py[i] - cy, px[i] - cx) + AVP_PI; ord[i] = i; }   // :215
+    for (int i = 0; i < n; ++i) { ang[i] = d_atan2(py[i] - cy, px[i] - cx) + AVP_PI; ord[i] = i; }   // :215
     for (int i = 1; i < n; ++i) { int t = ord[i], j = i; while (j > 0 && ang[ord[j - 1]] > ang[t]) { ord[j] = ord[j - 1]; --j; } ord[j] = t; }
     for (int j = 0; j < n; ++j) {
       const int a = ord[j], b = ord[(j + 1 == n) ? 0 : j + 1];
       const double p1x = px[a], p1y = py[a];
       const double vx = px[b] - p1x, vy = py[b] - p1y;
-      const double ra = atan2(vy, vx), c = avp_cos(ra), sn = avp_sin(ra);             // :229-232
+      const double ra = d_atan2(vy, vx), c = d_cos(ra), sn = d_sin(ra);             // :229-232
       const double len = __fma_rn(c, vx, sn * vy);     // np.dot(rotation_matrix, v)[0] (BLAS gemv)
       const int points_num = (int)floor(len / S.dx);                                   // :240-241
       const double lstep = (points_num > 1) ? len / (points_num - 1) : 0.0;
@@ -212,12 +212,12 @@ __global__ void k_expand_pure(avp_config cfg, const ScenDev *scen, int s, const 
   const double speed = fwd ? cfg.max_v : -cfg.max_v;
   const double th = pi_2_pi(pth + (cfg.max_v * tn) / cfg.lw * cfg.dt);
   const double td = speed * cfg.dt;
-  const double x_ = px + td * avp_cos(th), y_ = py + td * avp_sin(th);
+  const double x_ = px + td * d_cos(th), y_ = py + td * d_sin(th);
   int fl = 0;
   for (int k = 0; k < cfg.n_substeps; ++k) {
     const double th_i = pi_2_pi(pth + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
     const double td_i = speed * cfg.ddt * (k + 1);
-    if (check_pose_warp(cfg, S, cells + S.cell_off, col_start + S.col_off, px + td_i * avp_cos(th_i), py + td_i * avp_sin(th_i), th_i)) { fl |= 1; break; }
+    if (check_pose_warp(cfg, S, cells + S.cell_off, col_start + S.col_off, px + td_i * d_cos(th_i), py + td_i * d_sin(th_i), th_i)) { fl |= 1; break; }
   }
   if (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]) fl |= 2;
   const double q0[3] = {x_, y_, th}, q1[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
@@ -537,8 +537,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
           if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
           s_npops++;
           const Node &cn = nodes[ret];
-          const double ddx = cn.x - goal[0], ddy = cn.y - goal[1];
-          const double distance = sqrt(ddx * ddx + ddy * ddy);       // hybrid_a_star.py:308-309 (x*x for ** 2)
+          const double distance = sqrt(d_pow2(cn.x - goal[0]) + d_pow2(cn.y - goal[1]));   // hybrid_a_star.py:308-309 (** 2 == libm pow)
           s_in_radius = distance < cfg.flag_radius;
           s_shot_coll = 0; s_shot_bad = 0; s_npts = 0; s_best.ok = 0;
           s_ctl = CTL_RUN;
@@ -567,7 +566,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
         const double td = speed * cfg.dt;
         double th = cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt;
         th = pi_2_pi(th);
-        const double x_ = cn.x + td * avp_cos(th), y_ = cn.y + td * avp_sin(th);
+        const double x_ = cn.x + td * d_cos(th), y_ = cn.y + td * d_sin(th);
         s_cpose[i][0] = x_; s_cpose[i][1] = y_; s_cpose[i][2] = th;
         const int found = htab_find(htab, hmask, nodes, x_, y_, th);
         const bool in_closed = found >= 0 && nodes[found].in_closed;
@@ -601,7 +600,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
               const double td_i = speed * cfg.ddt * (k + 1);
               double th_i = cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1);
               th_i = pi_2_pi(th_i);
-              const double x_i = cn.x + td_i * avp_cos(th_i), y_i = cn.y + td_i * avp_sin(th_i);
+              const double x_i = cn.x + td_i * d_cos(th_i), y_i = cn.y + td_i * d_sin(th_i);
               if (check_pose_warp(cfg, S, cells, col_start, x_i, y_i, th_i)) { coll = 1; break; }
             }
             if (lane == 0) s_coll[i] = coll;
@@ -750,7 +749,7 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
             const double td_j = speed * cfg.ddt * (j + 1);
             double th_j = par.theta + (cfg.max_v * cfg.tan_steer[c.steer_idx]) / cfg.lw * cfg.ddt * (j + 1);
             th_j = pi_2_pi(th_j);
-            push(par.x + td_j * avp_cos(th_j), par.y + td_j * avp_sin(th_j), th_j);
+            push(par.x + td_j * d_cos(th_j), par.y + td_j * d_sin(th_j), th_j);
           }
         }
         R.n_astar = np_;

@@ -158,6 +158,22 @@ def perturbed_set(base: Scenario, count: int, seed: int, checker=None) -> List[S
     return out
 
 
+def perturbed_candidates(base: Scenario, m: int, seed: int) -> List[Scenario]:
+    """m draws of the C2 recipe WITHOUT the collision rule (batch-friendly: the caller checks all
+    candidates' start/goal poses at once, e.g. on the GPU, and keeps the first `count` free ones)."""
+    out = perturbed_set(base, m, seed, checker=None)
+    for i, s in enumerate(out):
+        s.name = f"{base.name}_c{i}"
+    return out
+
+
+def keep_collision_free(cands: Sequence[Scenario], start_collides, goal_collides, count: int) -> List[Scenario]:
+    out = [s for s, a, b in zip(cands, start_collides, goal_collides) if not (a or b)]
+    if len(out) < count:
+        raise RuntimeError(f"only {len(out)} of {len(cands)} candidates are collision free, need {count}")
+    return out[:count]
+
+
 def synthetic_map_obstacles(rng: np.random.Generator, n_poly: int = 256, extent: float = 20.0) -> List[np.ndarray]:
     """convex polygons with 3-8 vertices on a circle of radius U(0.10,0.35) m."""
     obs = []

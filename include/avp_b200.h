@@ -173,6 +173,12 @@ int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block)
  * hval[id] = distance of the first closedlist entry with grid_id == id, -1 if none. */
 int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *n_ids);
 
+/* CUDA-event stopwatch on the context's stream around any sequence of entry points, and the
+ * CUDA-event duration of the most recent search-kernel launch (bench.py timing legs) */
+int avp_timer_start(avp_ctx *ctx);
+int avp_timer_stop(avp_ctx *ctx, float *elapsed_ms);
+int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms);
+
 /* development aids: an in-kernel watchdog (SM clock cycles per scenario, 0 = off; a scenario
  * that exceeds it ends with AVP_CAPACITY) and the per-scenario progress checkpoints
  * (8 int32 each: phase, pops, len(closedlist), open size, ...).  The environment variable

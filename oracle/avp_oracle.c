@@ -574,12 +574,14 @@ int orc_rs_words(const double q0[3], const double q1[3], double maxc, int xy_np,
 }
 int orc_rs_optimal(const double q0[3], const double q1[3], double maxc, double step_size, int xy_np, int phi_np, int32_t *nseg, double *lengths, char *ctypes, double *L,
                    int cap, double *x, double *y, double *yaw, int32_t *dir, int32_t *n_pts) {
-  static rs_result r; calc_optimal_path(q0, q1, maxc, step_size, 1, xy_np, phi_np, &r);
-  if (!r.ok) return r.degenerate ? -2 : -1;
+  rs_result *rp = malloc(sizeof(rs_result)); calc_optimal_path(q0, q1, maxc, step_size, 1, xy_np, phi_np, rp);
+#define r (*rp)
+  if (!r.ok) { int rc_ = r.degenerate ? -2 : -1; free(rp); return rc_; }
   *nseg = r.w.n; memcpy(lengths, r.w.len, sizeof(double) * r.w.n); memset(ctypes, 0, 8); strcpy(ctypes, r.w.ct); *L = r.w.L;
   *n_pts = r.c.n;
   for (int i = 0; i < r.c.n && i < cap; ++i) { x[i] = r.c.x[i]; y[i] = r.c.y[i]; yaw[i] = r.c.yaw[i]; dir[i] = r.c.dir[i]; }
-  return r.degenerate ? 1 : 0;
+  { int rc_ = r.degenerate ? 1 : 0; free(rp); return rc_; }
+#undef r
 }
 
 /* ------------------------------------------------------------------ Dijkstra (path_plan/compute_h.py) */
@@ -701,6 +703,7 @@ typedef struct {
   int n_closed, global_index;
   double goal[3];
   int n_hq, n_hcalls;
+  void *rsbuf;                      /* scratch rs_result */
   int64_t *hq_log; int hq_cap;      /* (terminate id, dist, closed_len) per compute_path call */
   int status;
 } astar;
@@ -755,9 +758,9 @@ static double calc_node_heuristic(astar *A, const onode *n) {
   if (id >= 0 && id < A->dij->n_ids && A->dij->hval[id] >= 0) h1 = A->dij->hval[id];
   else { h1 = dij_query(A, n->x, n->y); if (h1 < 0) return 0.0; }
   double q0[3] = {n->x, n->y, n->theta};
-  static rs_result r; calc_optimal_path(q0, A->goal, 1 / A->cfg->min_radius_turn, 0.5, 0, 1, n->index != 0, &r);
-  if (r.degenerate || !r.ok) { A->status = AVP_RS_DEGENERATE; return 0.0; }
-  double h2 = r.w.L, hv1 = h1 / 100.0;
+  rs_result *rp = A->rsbuf; calc_optimal_path(q0, A->goal, 1 / A->cfg->min_radius_turn, 0.5, 0, 1, n->index != 0, rp);
+  if (rp->degenerate || !rp->ok) { A->status = AVP_RS_DEGENERATE; return 0.0; }
+  double h2 = rp->w.L, hv1 = h1 / 100.0;
   return (h2 > hv1) ? h2 : hv1;   /* max(h_value_1, h_value_2) */
 }
 
@@ -821,6 +824,7 @@ typedef struct orc_plan_out {
   double *final_path; int cap_path;    /* rows x,y,theta */
   double *rs_x, *rs_y, *rs_yaw; int32_t *rs_dir; int cap_rs;
   int64_t *hq_log; int cap_hq;
+  int32_t *hval_out; long hval_cap;    /* final h table (first closedlist distance per grid id), may be NULL */
 } orc_plan_out;
 
 /* PathPlanner.a_star_plan (path_planner.py:58-110) incl. hybrid_a_star.__init__ (:72-124),
@@ -834,6 +838,9 @@ int orc_plan(const orc_map *m, const avp_config *cfg, orc_plan_out *out) {
   A.hcap = A.ncap; A.heap = malloc(sizeof(int32_t) * A.hcap);
   int hb = 1; while (hb < 2 * A.ncap) hb <<= 1; A.hmask = hb - 1; A.htab = malloc(sizeof(int32_t) * hb); memset(A.htab, 0xff, sizeof(int32_t) * hb);
   A.hq_log = out->hq_log; A.hq_cap = out->hq_log ? out->cap_hq : 0;
+  A.rsbuf = malloc(sizeof(rs_result));
+  rs_result *rsp = calloc(1, sizeof(rs_result));
+#define rs (*rsp)
   avp_plan_summary *S = &out->sum; memset(S, 0, sizeof(*S));
   S->nx = m->nx; S->ny = m->ny; S->n_obs = m->n_obs; S->pitch[0] = m->dx; S->pitch[1] = m->dy;
   memcpy(S->boundary, m->boundary, sizeof(double) * 4); S->origin[0] = m->boundary[0]; S->origin[1] = m->boundary[2];
@@ -846,7 +853,6 @@ int orc_plan(const orc_map *m, const avp_config *cfg, orc_plan_out *out) {
   htab_insert(&A, 0); open_put(&A, 0);
 
   int reach_goal = 0, cur = -1, in_radius = 0, collision = 0, n_pops = 0;
-  static rs_result rs;
   double maxc = 1 / cfg->min_radius_turn;
   while (A.hn > 0 && !reach_goal) {                              /* path_planner.py:68 */
     if (n_pops >= max_pops) { A.status = AVP_CAPACITY; break; }
@@ -909,8 +915,10 @@ int orc_plan(const orc_map *m, const avp_config *cfg, orc_plan_out *out) {
 done:
   S->status = A.status; S->global_index = A.global_index; S->n_closed = A.n_closed; S->n_open = A.hn;
   S->n_hq = A.n_hq; S->h_closed = (int32_t)A.dij->closed_len; S->n_hcalls = A.n_hcalls;
-  orc_dij_free(A.dij); free(A.nodes); free(A.heap); free(A.htab);
+  if (out->hval_out) for (long i = 0; i < A.dij->n_ids && i < out->hval_cap; ++i) out->hval_out[i] = A.dij->hval[i];
+  orc_dij_free(A.dij); free(A.nodes); free(A.heap); free(A.htab); free(A.rsbuf); free(rsp);
   return 0;
+#undef rs
 }
 
 /* rollout + collision flags + rs length of the 2n successors of one pose: the pure part of
@@ -918,6 +926,7 @@ done:
 void orc_expand_pure(const orc_map *m, const avp_config *c, const double parent[3], double *out_pose, int32_t *out_flags, double *out_rsL) {
   const double *b = m->boundary; int ns = c->steering_angle_num;
   double goal[3] = {m->pose[3], m->pose[4], pi_2_pi(m->pose[5])};
+  rs_result *rp = malloc(sizeof(rs_result));
   for (int i = 0; i < 2 * ns; ++i) {
     double tn = c->tan_steer[i % ns]; int fwd = i < ns; double speed = fwd ? c->max_v : -c->max_v;
     double th = pi_2_pi(parent[2] + (c->max_v * tn) / c->lw * c->dt);
@@ -931,9 +940,10 @@ void orc_expand_pure(const orc_map *m, const avp_config *c, const double parent[
     }
     if (x_ > b[1] || x_ < b[0] || y_ > b[3] || y_ < b[2]) fl |= 2;
     out_flags[i] = fl;
-    double q0[3] = {x_, y_, th}; static rs_result r; calc_optimal_path(q0, goal, 1 / c->min_radius_turn, 0.5, 0, 1, 1, &r);
-    out_rsL[i] = r.ok ? r.w.L : NAN;
+    double q0[3] = {x_, y_, th}; calc_optimal_path(q0, goal, 1 / c->min_radius_turn, 0.5, 0, 1, 1, rp);
+    out_rsL[i] = rp->ok ? rp->w.L : NAN;
   }
+  free(rp);
 }
 
 double orc_py_hypot(double a, double b) { return py_hypot(a, b); }

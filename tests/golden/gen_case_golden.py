@@ -32,7 +32,11 @@ from map import costmap  # noqa: E402
 from path_plan import path_planner  # noqa: E402
 
 
-def run_case(csv_path, out_path, max_seconds=None):
+class _Truncate(Exception):
+    pass
+
+
+def run_case(csv_path, out_path, max_pops=None):
     cfg = ref_shim.default_config()
     rec = {}
     t0 = time.time()
@@ -72,6 +76,8 @@ def run_case(csv_path, out_path, max_seconds=None):
     orig_trg = astar.try_reach_goal
 
     def trg(node):
+        if max_pops is not None and len(pops) >= max_pops:
+            raise _Truncate()          # Cases 7, 8, 19 never finish in the reference: pin a prefix
         pops.append(int(node.index))
         pop_state.append((float(node.x), float(node.y), float(node.theta)))
         pop_fgh.append((float(node.f), float(node.g), float(node.h)))
@@ -111,6 +117,8 @@ def run_case(csv_path, out_path, max_seconds=None):
     except AttributeError as e:  # open list exhausted (path_planner.py:104)
         status = 'open_exhausted'
         err = repr(e)
+    except _Truncate:
+        status = 'truncated'
     t_search = time.time() - t2
 
     rec['status'] = np.array(status)
@@ -153,13 +161,14 @@ def main():
     ap.add_argument('cases', nargs='*')
     ap.add_argument('--csv')
     ap.add_argument('--out')
+    ap.add_argument('--max-pops', type=int, default=None)
     a = ap.parse_args()
     if a.csv:
-        run_case(a.csv, os.path.join(HERE, 'cases', a.out + '.npz'))
+        run_case(a.csv, os.path.join(HERE, 'cases', a.out + '.npz'), a.max_pops)
         return
     for c in a.cases:
         run_case(os.path.join(ref_shim.REF_ROOT, 'BenchmarkCases', c + '.csv'),
-                 os.path.join(HERE, 'cases', c + '.npz'))
+                 os.path.join(HERE, 'cases', c + '.npz'), a.max_pops)
 
 
 if __name__ == '__main__':

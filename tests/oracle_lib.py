@@ -28,6 +28,7 @@ class PlanOut(ctypes.Structure):
         ("final_path", c_dp), ("cap_path", ctypes.c_int),
         ("rs_x", c_dp), ("rs_y", c_dp), ("rs_yaw", c_dp), ("rs_dir", c_ip), ("cap_rs", ctypes.c_int),
         ("hq_log", c_lp), ("cap_hq", ctypes.c_int),
+        ("hval_out", c_ip), ("hval_cap", ctypes.c_long),
     ]
 
 
@@ -210,7 +211,7 @@ def rs_optimal(q0, q1, maxc, step=0.5, cap=2048, xy_np=1, phi_np=1):
                 x=x[:n].copy(), y=y[:n].copy(), yaw=yaw[:n].copy(), directions=d[:n].copy())
 
 
-def plan(m: OracleMap, cfg, cap_pops=None, cap_path=4096):
+def plan(m: OracleMap, cfg, cap_pops=None, cap_path=4096, want_hval=False):
     cap_pops = cap_pops or max(1, cfg.max_pops)
     out = PlanOut()
     pops = np.zeros(cap_pops, dtype=np.int32)
@@ -225,6 +226,10 @@ def plan(m: OracleMap, cfg, cap_pops=None, cap_path=4096):
     out.final_path, out.cap_path = _dp(fp), cap_path
     out.rs_x, out.rs_y, out.rs_yaw, out.rs_dir, out.cap_rs = _dp(rs_x), _dp(rs_y), _dp(rs_yaw), _ip(rs_dir), 2048
     out.hq_log, out.cap_hq = hq.ctypes.data_as(c_lp), 4096
+    hval = None
+    if want_hval:
+        hval = np.full((m.nx + 4) * (m.ny + 4) + 64, -1, dtype=np.int32)
+        out.hval_out, out.hval_cap = _ip(hval), hval.size
     lib().orc_plan(m._h, ctypes.byref(cfg), ctypes.byref(out))
     s = out.sum
     npop = min(s.n_pops, cap_pops)
@@ -234,4 +239,4 @@ def plan(m: OracleMap, cfg, cap_pops=None, cap_path=4096):
                 n_hcalls=s.n_hcalls, pops=pops[:npop].copy(), pop_state=pop_state[:npop].copy(),
                 pop_fgh=pop_fgh[:npop].copy(), final_path=fp[:min(s.n_final, cap_path)].copy(),
                 rs_x=rs_x[:s.n_rs].copy(), rs_y=rs_y[:s.n_rs].copy(), rs_yaw=rs_yaw[:s.n_rs].copy(),
-                rs_dir=rs_dir[:s.n_rs].copy(), hq=hq[:min(s.n_hq, 4096)].copy(), last_index=s.last_index)
+                rs_dir=rs_dir[:s.n_rs].copy(), hq=hq[:min(s.n_hq, 4096)].copy(), last_index=s.last_index, hval=hval)
