@@ -235,6 +235,16 @@ class DevicePlanner:
         self._ck(self._L.avp_last_search_ms(self._h, ctypes.byref(ms)), "avp_last_search_ms")
         return float(ms.value)
 
+    def last_search_passes(self):
+        a, b, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_int32()
+        self._ck(self._L.avp_last_search_passes(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)), "avp_last_search_passes")
+        return float(a.value), float(b.value), int(n.value) % 100000, int(n.value) // 100000
+
+    def phase_profile(self) -> np.ndarray:
+        out = np.zeros((self.n, 8), dtype=np.int64)
+        self._ck(self._L.avp_fetch_profile(self._h, out.ctypes.data_as(_native.c_lp)), "avp_fetch_profile")
+        return out
+
     def set_watchdog(self, cycles: int):
         self._ck(self._L.avp_set_watchdog(self._h, int(cycles)), "avp_set_watchdog")
 

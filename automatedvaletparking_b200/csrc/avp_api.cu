@@ -31,12 +31,15 @@ struct avp_ctx {
   int32_t *d_hval = nullptr, *d_ost = nullptr; double *d_gx = nullptr, *d_gy = nullptr;
   // per-slot workspaces
   int ws_slots = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
-  Node *d_nodes = nullptr; int32_t *d_oheap = nullptr, *d_htab = nullptr; unsigned long long *d_dheap = nullptr;
+  Node *d_nodes = nullptr; int32_t *d_oheap = nullptr, *d_htab = nullptr; unsigned long long *d_dheap = nullptr; double *d_oheap_f = nullptr;
+  int slots_wide = 0; int slots_w[3] = {0, 0, 0}; int32_t *d_worklist = nullptr; int worklist_cap = 0;
   double *d_course = nullptr; int32_t *d_course_dir = nullptr;
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
+  long long *d_prof = nullptr;
   int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
+  float pass_ms[2] = {0.f, 0.f}; int n_pending = 0; int wide_block = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
   // scratch for the small API kernels
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -70,8 +73,13 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, AVP_BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-  ctx->slots = ctx->n_sm * per_sm;               // persistent grid: a multiple of the SM count
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<AVP_BLOCK_NARROW>, AVP_BLOCK_NARROW, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  ctx->slots = ctx->n_sm * per_sm;               // persistent grids: multiples of the SM count
+  int o = 0;
+  ctx->slots_w[0] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<512>, 512, 0) == cudaSuccess && o > 0) ? o : 1);
+  ctx->slots_w[1] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<256>, 256, 0) == cudaSuccess && o > 0) ? o : 1);
+  ctx->slots_w[2] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<128>, 128, 0) == cudaSuccess && o > 0) ? o : 1);
+  ctx->slots_wide = ctx->slots_w[0];
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
   *out = ctx;
@@ -86,12 +94,12 @@ static void free_scenarios(avp_ctx *ctx) {
   ctx->n = 0; ctx->rasterised = false;
 }
 static void free_results(avp_ctx *ctx) {
-  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq); free_dev(ctx->d_dbg); ctx->d_dbg = nullptr;
+  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq); free_dev(ctx->d_dbg); ctx->d_dbg = nullptr; free_dev(ctx->d_prof); ctx->d_prof = nullptr;
   ctx->d_sums = nullptr; ctx->d_paths = nullptr; ctx->d_pops = nullptr; ctx->d_hq = nullptr; ctx->res_n = 0;
 }
 static void free_ws(avp_ctx *ctx) {
-  free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir);
-  ctx->d_nodes = nullptr; ctx->d_oheap = ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
+  free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir); free_dev(ctx->d_oheap_f);
+  ctx->d_oheap_f = nullptr; ctx->d_nodes = nullptr; ctx->d_oheap = ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
 }
 
 extern "C" int avp_destroy(avp_ctx *ctx) {
@@ -99,7 +107,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
-  free_dev(ctx->d_counter); free_dev(ctx->d_scratch);
+  free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_worklist);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->evA) cudaEventDestroy(ctx->evA); if (ctx->evB) cudaEventDestroy(ctx->evB);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -284,6 +292,7 @@ static int ensure_ws(avp_ctx *ctx) {
   const int S = ctx->slots;   // allocate for the full persistent grid once
   CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)S * node_cap));
   CK(cudaMalloc(&ctx->d_oheap, sizeof(int32_t) * (size_t)S * node_cap));
+  CK(cudaMalloc(&ctx->d_oheap_f, sizeof(double) * (size_t)S * node_cap));
   CK(cudaMalloc(&ctx->d_htab, sizeof(int32_t) * (size_t)S * hb));
   CK(cudaMalloc(&ctx->d_dheap, sizeof(unsigned long long) * (size_t)S * ctx->dheap_cap));
   CK(cudaMalloc(&ctx->d_course, sizeof(double) * (size_t)S * 3 * AVP_COURSE_CAP));
@@ -301,11 +310,43 @@ static int ensure_results(avp_ctx *ctx, int cap_path, int cap_pops) {
   CK(cudaMalloc(&ctx->d_pops, sizeof(int32_t) * n * (size_t)(cap_pops > 0 ? cap_pops : 1)));
   CK(cudaMalloc(&ctx->d_hq, sizeof(int32_t) * n * AVP_HQ_CAP * 3));
   CK(cudaMalloc(&ctx->d_dbg, sizeof(int) * n * 8));
+  CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * n * 8));
+  CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * n * 8));
   CK(cudaMemset(ctx->d_dbg, 0, sizeof(int) * n * 8));
   ctx->res_n = ctx->n; ctx->cap_path = cap_path; ctx->cap_pops = cap_pops;
   return 0;
 }
 
+static int wait_search(avp_ctx *ctx, cudaEvent_t ev) {
+  const char *lim = getenv("AVP_HOST_TIMEOUT_S");        // development aid: never wait forever on a kernel
+  if (lim && atof(lim) > 0) {
+    const double limit = atof(lim);
+    timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (;;) {
+      cudaError_t q = cudaEventQuery(ev);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) { ctx->err = std::string("k_search: ") + cudaGetErrorString(q); return -1; }
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > limit) {
+        std::vector<int> dbg((size_t)ctx->n * 8, 0);
+        cudaMemcpy(dbg.data(), ctx->d_dbg, sizeof(int) * dbg.size(), cudaMemcpyDeviceToHost);
+        std::string msg = "k_search timed out; unfinished scenarios (id: phase,pops,h_closed,open):";
+        int shown = 0;
+        for (int i = 0; i < ctx->n && shown < 32; ++i) if (dbg[8 * i] != 9) { char b[96]; snprintf(b, sizeof b, " [%d: %d,%d,%d,%d]", i, dbg[8 * i], dbg[8 * i + 1], dbg[8 * i + 2], dbg[8 * i + 3]); msg += b; ++shown; }
+        ctx->err = msg;
+        return -11;
+      }
+      timespec ts = {0, 1000000}; nanosleep(&ts, nullptr);
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+/* Two passes.  Pass 1: every scenario on narrow CTAs (many concurrent scenarios: the eager
+ * Dijkstra and short searches dominate) with a pop budget.  Pass 2: the scenarios that ran out of
+ * budget are re-planned from scratch on wide CTAs, where the per-pop latency is ~BLOCK-parallel.
+ * Results are identical to a single pass (a search is a deterministic function of its scenario). */
 static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   if (ctx->n <= 0) FAIL("plan: no scenarios uploaded");
   if (!ctx->rasterised) FAIL("plan: call avp_rasterise first");
@@ -315,38 +356,58 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.cfg = ctx->cfg; if (P.cfg.max_pops <= 0) P.cfg.max_pops = 20000;
   P.n_scen = ctx->n; P.scen = ctx->d_scen; P.cost = ctx->d_cost; P.cells = ctx->d_cells; P.col_start = ctx->d_col;
   P.hval = ctx->d_hval; P.ost = ctx->d_ost; P.gx = ctx->d_gx; P.gy = ctx->d_gy;
-  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap;
+  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.oheap_f = ctx->d_oheap_f;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
-  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.watchdog_cycles = ctx->watchdog_cycles;
+  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.watchdog_cycles = ctx->watchdog_cycles;
+  const char *pb = getenv("AVP_POP_BUDGET");
+  const int budget = pb ? atoi(pb) : 192;
+  P.work_list = nullptr; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_search<<<grid, AVP_BLOCK, 0, ctx->stream>>>(P); ctx->launches++;
+  k_search<AVP_BLOCK_NARROW><<<grid, AVP_BLOCK_NARROW, 0, ctx->stream>>>(P); ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());
-  const char *lim = getenv("AVP_HOST_TIMEOUT_S");        // development aid: never wait forever on a kernel
-  if (lim && atof(lim) > 0) {
-    const double limit = atof(lim);
-    timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (;;) {
-      cudaError_t q = cudaEventQuery(ctx->ev1);
-      if (q == cudaSuccess) break;
-      if (q != cudaErrorNotReady) { ctx->err = std::string("k_search: ") + cudaGetErrorString(q); return -1; }
-      clock_gettime(CLOCK_MONOTONIC, &t1);
-      if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > limit) {
-        std::vector<int> dbg((size_t)ctx->n * 8, 0);
-        cudaMemcpy(dbg.data(), ctx->d_dbg, sizeof(int) * dbg.size(), cudaMemcpyDeviceToHost);
-        std::string msg = "k_search timed out; per-scenario (phase,pops,h_closed,open):";
-        for (int i = 0; i < ctx->n && i < 64; ++i) { char b[96]; snprintf(b, sizeof b, " [%d: %d,%d,%d,%d]", i, dbg[8 * i], dbg[8 * i + 1], dbg[8 * i + 2], dbg[8 * i + 3]); msg += b; }
-        ctx->err = msg;
-        return -11;
-      }
-      timespec ts = {0, 2000000}; nanosleep(&ts, nullptr);
+  if (wait_search(ctx, ctx->ev1)) return -1;
+  float ms1 = 0.f, ms2 = 0.f;
+  CK(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1));
+  ctx->pass_ms[0] = ms1; ctx->pass_ms[1] = 0.f; ctx->n_pending = 0;
+  if (P.pop_budget < P.cfg.max_pops) {
+    std::vector<avp_plan_summary> hs(ctx->n);
+    CK(cudaMemcpyAsync(hs.data(), ctx->d_sums, sizeof(avp_plan_summary) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> list;
+    for (int i = 0; i < ctx->n; ++i) if (hs[i].status == AVP_PENDING) list.push_back(i);
+    ctx->n_pending = (int)list.size();
+    if (!list.empty()) {
+      if ((int)list.size() > ctx->worklist_cap) { free_dev(ctx->d_worklist); ctx->d_worklist = nullptr; CK(cudaMalloc(&ctx->d_worklist, sizeof(int32_t) * list.size())); ctx->worklist_cap = (int)list.size(); }
+      CK(cudaMemcpyAsync(ctx->d_worklist, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+      P.work_list = ctx->d_worklist; P.n_work = (int)list.size(); P.pop_budget = P.cfg.max_pops;
+      // widest CTA whose persistent grid still holds every pending scenario at once (one wave)
+      const int npend = (int)list.size();
+      int which = 3;
+      for (int w = 0; w < 3; ++w) if (npend <= ctx->slots_w[w] && npend <= ctx->ws_slots) { which = w; break; }
+      const char *fw = getenv("AVP_WIDE_BLOCK");
+      if (fw) { const int b = atoi(fw); which = b == 512 ? 0 : b == 256 ? 1 : b == 128 ? 2 : 3; }
+      int cap = which < 3 ? ctx->slots_w[which] : ctx->slots;
+      int grid2 = cap; if (grid2 > npend) grid2 = npend; if (grid2 > ctx->ws_slots) grid2 = ctx->ws_slots;
+      ctx->wide_block = which == 0 ? 512 : which == 1 ? 256 : which == 2 ? 128 : AVP_BLOCK_NARROW;
+      CK(cudaEventRecord(ctx->ev0, ctx->stream));
+      if (which == 0) k_search<512><<<grid2, 512, 0, ctx->stream>>>(P);
+      else if (which == 1) k_search<256><<<grid2, 256, 0, ctx->stream>>>(P);
+      else if (which == 2) k_search<128><<<grid2, 128, 0, ctx->stream>>>(P);
+      else k_search<AVP_BLOCK_NARROW><<<grid2, AVP_BLOCK_NARROW, 0, ctx->stream>>>(P);
+      ctx->launches++;
+      CK(cudaEventRecord(ctx->ev1, ctx->stream));
+      CK(cudaGetLastError());
+      if (wait_search(ctx, ctx->ev1)) return -1;
+      CK(cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev1));
+      ctx->pass_ms[1] = ms2;
     }
   }
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  if (elapsed_ms) *elapsed_ms = ms1 + ms2;
   return 0;
 }
 
@@ -419,7 +480,7 @@ extern "C" int avp_fetch_hq_log(avp_ctx *ctx, int s, int32_t *log3, int cap_entr
 
 extern "C" int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block) {
   if (!ctx) return -3;
-  if (n_sm) *n_sm = ctx->n_sm; if (slots) *slots = ctx->slots; if (block) *block = AVP_BLOCK;
+  if (n_sm) *n_sm = ctx->n_sm; if (slots) *slots = ctx->slots; if (block) *block = AVP_BLOCK_NARROW;
   return 0;
 }
 
@@ -455,7 +516,23 @@ extern "C" int avp_timer_stop(avp_ctx *ctx, float *elapsed_ms) {
 /* CUDA-event duration of the most recent search kernel launch */
 extern "C" int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms) {
   if (!ctx) return -3;
+  if (elapsed_ms) *elapsed_ms = ctx->pass_ms[0] + ctx->pass_ms[1];
+  return 0;
+}
+/* per-pass CUDA-event times of the last search and the number of scenarios handed to pass 2 */
+extern "C" int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_pass2, int32_t *n_pass2) {
+  if (!ctx) return -3;
+  if (ms_pass1) *ms_pass1 = ctx->pass_ms[0]; if (ms_pass2) *ms_pass2 = ctx->pass_ms[1]; if (n_pass2) *n_pass2 = ctx->n_pending + 100000 * ctx->wide_block;
+  return 0;
+}
+
+/* per-scenario SM-cycle accumulators of the search kernel's phases (thread 0 of the CTA):
+ * [0] init + eager Dijkstra, [1] loop top, [2] heappop + poses/queries, [3] lookups + collision checks +
+ * rs instances, [4] selection + course plan, [5] course + shot check, [6] commit, [7] commit preparation */
+extern "C" int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n) {
+  if (!ctx) return -3;
+  if (!ctx->d_prof) FAIL("avp_fetch_profile: no results");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  CK(cudaMemcpy(out8n, ctx->d_prof, sizeof(long long) * (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
   return 0;
 }

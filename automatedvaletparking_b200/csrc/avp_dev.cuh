@@ -82,8 +82,18 @@ __device__ __noinline__ double py_hypot(double a, double b) {
 }
 
 // Python float % (Objects/floatobject.c float_rem); fmod is exact
+// fmod(v, w) for w > 0, exact: each subtraction below is exact by Sterbenz' lemma
+// (r in [k*w, 2*k*w] minus k*w, k a power of two), so the result equals the exact remainder.
+__device__ __forceinline__ double fmod_small(double v, double w) {
+  double r = fabs(v);
+  if (r >= 8.0 * w) return fmod(v, w);
+  if (r >= 4.0 * w) r -= 4.0 * w;
+  if (r >= 2.0 * w) r -= 2.0 * w;
+  if (r >= w) r -= w;
+  return copysign(r, v);
+}
 __device__ __forceinline__ double py_mod(double v, double w) {
-  double m = fmod(v, w);
+  double m = fmod_small(v, w);
   if (m != 0.0) { if ((w < 0) != (m < 0)) m += w; } else m = copysign(0.0, w);
   return m;
 }
@@ -141,8 +151,7 @@ struct VehGeom {
   double lk[4], lb[4], ls[4];   // slope, intercept, sqrt(1+k^2) of the 4 boundary lines
 };
 
-__device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y, double th, VehGeom &g) {
-  const double cs = d_cos(th), sn = d_sin(th);
+__device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y, double cs, double sn, VehGeom &g) {
   const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
   const double lx0 = -c.lr - fr, lx1 = c.lw + c.lf + fr, ly0 = -c.lb / 2 - sd, ly1 = c.lb / 2 + sd;
   const double locx[4] = {lx0, lx1, lx1, lx0}, locy[4] = {ly0, ly0, ly1, ly1};
@@ -213,10 +222,10 @@ __device__ __forceinline__ void col_range(const ScenDev &S, double x_min, double
 // distance_checker.check (collision_check.py:144-240), warp-collective: all 32 lanes call it
 // with the same pose; returns the same bool on every lane.
 __device__ __forceinline__ bool check_distance_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
-                                                    const int32_t *col_start, double x, double y, double th) {
+                                                    const int32_t *col_start, double x, double y, double cs, double sn) {
   const int lane = threadIdx.x & 31;
   VehGeom g;
-  veh_geom(c, x, y, th, g);
+  veh_geom(c, x, y, cs, sn, g);
   int lo, hi;
   col_range(S, g.x_min, g.x_max, lo, hi);
   if (lo > hi) return false;
@@ -236,11 +245,10 @@ __device__ __forceinline__ bool check_distance_warp(const avp_config &c, const S
 
 // two_circle_checker.check (collision_check.py:88-137), warp-collective
 __device__ __forceinline__ bool check_circle_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
-                                                  double x, double y, double th) {
+                                                  double x, double y, double cs, double sn) {
   const int lane = threadIdx.x & 31;
   const double h2 = (c.lr + c.lw + c.lf) / 2;
   const double Rd = 0.5 * sqrt(d_pow2(h2) + d_pow2(c.lb));
-  const double cs = d_cos(th), sn = d_sin(th);
   const double kf = 1.0 / 4 * (3 * c.lw + 3 * c.lf - c.lr), kr = 1.0 / 4 * (c.lw + c.lf - 3 * c.lr);
   const double fx = x + kf * cs, fy = y + kf * sn, rx = x + kr * cs, ry = y + kr * sn;
   double right, left, upper, down;
@@ -261,10 +269,15 @@ __device__ __forceinline__ bool check_circle_warp(const avp_config &c, const Sce
   return hit;
 }
 
+// cs, sn = cos(theta), sin(theta) of the pose (np.cos/np.sin in create_anticlockpoint, costmap.py:90-91)
+__device__ __forceinline__ bool check_pose_cs_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
+                                                   const int32_t *col_start, double x, double y, double cs, double sn) {
+  return c.collision_mode == 1 ? check_circle_warp(c, S, cells, x, y, cs, sn)
+                               : check_distance_warp(c, S, cells, col_start, x, y, cs, sn);
+}
 __device__ __forceinline__ bool check_pose_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
                                                 const int32_t *col_start, double x, double y, double th) {
-  return c.collision_mode == 1 ? check_circle_warp(c, S, cells, x, y, th)
-                               : check_distance_warp(c, S, cells, col_start, x, y, th);
+  return check_pose_cs_warp(c, S, cells, col_start, x, y, d_cos(th), d_sin(th));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -298,14 +311,14 @@ __device__ __forceinline__ bool rs_SLS(double x, double y, double phi, double &t
   return false;
 }
 // rs_curve.py:159-167
-__device__ __forceinline__ bool rs_LSL(double x, double y, double phi, double &t, double &u, double &v) {
-  double uu, tt; rs_R(x - d_sin(phi), y - 1.0 + d_cos(phi), uu, tt);
+__device__ __forceinline__ bool rs_LSL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  double uu, tt; rs_R(x - sphi, y - 1.0 + cphi, uu, tt);
   if (tt >= 0.0) { const double vv = rs_M(phi - tt); if (vv >= 0.0) { t = tt; u = uu; v = vv; return true; } }
   return false;
 }
 // rs_curve.py:170-183
-__device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double &t, double &u, double &v) {
-  double u1, t1; rs_R(x + d_sin(phi), y - 1.0 - d_cos(phi), u1, t1);
+__device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  double u1, t1; rs_R(x + sphi, y - 1.0 - cphi, u1, t1);
   u1 = d_pow2(u1);                                                 // u1 ** 2 == libm pow(u1, 2.0)
   if (u1 >= 4.0) {
     const double uu = sqrt(u1 - 4.0), theta = d_atan2(2.0, uu), tt = rs_M(t1 + theta), vv = rs_M(tt - phi);
@@ -314,8 +327,8 @@ __device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double &t
   return false;
 }
 // rs_curve.py:186-197
-__device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double &t, double &u, double &v) {
-  double u1, t1; rs_R(x - d_sin(phi), y - 1.0 + d_cos(phi), u1, t1);
+__device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  double u1, t1; rs_R(x - sphi, y - 1.0 + cphi, u1, t1);
   if (u1 <= 4.0) {
     const double uu = -2.0 * d_asin(0.25 * u1), tt = rs_M(t1 + 0.5 * uu + AVP_PI), vv = rs_M(phi - tt + uu);
     if (tt >= 0.0 && uu <= 0.0) { t = tt; u = uu; v = vv; return true; }
@@ -331,8 +344,8 @@ __device__ __forceinline__ void rs_tauOmega(double u, double v, double xi, doubl
   omega = rs_M(tau - u + v - phi);
 }
 // rs_curve.py:326-337
-__device__ __forceinline__ bool rs_LRLRn(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi), rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
+__device__ __forceinline__ bool rs_LRLRn(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  const double xi = x + sphi, eta = y - 1.0 - cphi, rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
   if (rho <= 1.0) {
     const double uu = d_acos(rho); double tt, vv; rs_tauOmega(uu, -uu, xi, eta, phi, tt, vv);
     if (tt >= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
@@ -340,8 +353,8 @@ __device__ __forceinline__ bool rs_LRLRn(double x, double y, double phi, double 
   return false;
 }
 // rs_curve.py:340-352
-__device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi), rho = (20.0 - xi * xi - eta * eta) / 16.0;
+__device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  const double xi = x + sphi, eta = y - 1.0 - cphi, rho = (20.0 - xi * xi - eta * eta) / 16.0;
   if (0.0 <= rho && rho <= 1.0) {
     const double uu = -d_acos(rho);
     if (uu >= -0.5 * AVP_PI) {
@@ -352,8 +365,8 @@ __device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double 
   return false;
 }
 // rs_curve.py:391-403
-__device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi); double rho, theta; rs_R(-eta, xi, rho, theta);
+__device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  const double xi = x + sphi, eta = y - 1.0 - cphi; double rho, theta; rs_R(-eta, xi, rho, theta);
   if (rho >= 2.0) {
     const double tt = theta, uu = 2.0 - rho, vv = rs_M(tt + 0.5 * AVP_PI - phi);
     if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
@@ -361,8 +374,8 @@ __device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double &
   return false;
 }
 // rs_curve.py:406-419
-__device__ __forceinline__ bool rs_LRSL(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x - d_sin(phi), eta = y - 1.0 + d_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
+__device__ __forceinline__ bool rs_LRSL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  const double xi = x - sphi, eta = y - 1.0 + cphi; double rho, theta; rs_R(xi, eta, rho, theta);
   if (rho >= 2.0) {
     const double r = sqrt(rho * rho - 4.0), uu = 2.0 - r, tt = rs_M(theta + d_atan2(r, -2.0)), vv = rs_M(phi - 0.5 * AVP_PI - tt);
     if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
@@ -370,8 +383,8 @@ __device__ __forceinline__ bool rs_LRSL(double x, double y, double phi, double &
   return false;
 }
 // rs_curve.py:494-510
-__device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double &t, double &u, double &v) {
-  const double xi = x + d_sin(phi), eta = y - 1.0 - d_cos(phi); double rho, theta; rs_R(xi, eta, rho, theta);
+__device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
+  const double xi = x + sphi, eta = y - 1.0 - cphi; double rho, theta; rs_R(xi, eta, rho, theta);
   if (rho >= 2.0) {
     const double uu = 4.0 - sqrt(rho * rho - 4.0);
     if (uu <= 0.0) {
@@ -383,12 +396,13 @@ __device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double 
 }
 
 // normalised query of generate_path (rs_curve.py:627-634)
-struct RsQuery { double x, y, phi, xb, yb; };
+struct RsQuery { double x, y, phi, xb, yb, sp, cp; };   // sp, cp = sin(phi), cos(phi): sin(-phi) = -sp, cos(-phi) = cp bit for bit
 __device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
   const double dx = q1[0] - q0[0], dy = q1[1] - q0[1], dth = q1[2] - q0[2];
   const double c = d_cos(q0[2]), s = d_sin(q0[2]);
   Q.x = (c * dx + s * dy) * maxc; Q.y = (-s * dx + c * dy) * maxc; Q.phi = dth;
   const double cp = d_cos(dth), sp = d_sin(dth);
+  Q.sp = sp; Q.cp = cp;
   Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;          // rs_curve.py:286-287, :456-457
 }
 
@@ -398,16 +412,17 @@ __device__ __forceinline__ bool rs_eval_instance(int inst, const RsQuery &Q, dou
   const int r = (inst - 2) & 3, fam = (inst - 2) >> 2;   // fam 0 LSL,1 LSR,2 LRL,3 LRLb,4 LRLRn,5 LRLRp,6 LRSL,7 LRSR,8 LRSLb,9 LRSRb,10 LRSLR
   const bool back = (fam == 3 || fam == 8 || fam == 9);
   const double bx = back ? Q.xb : Q.x, by = back ? Q.yb : Q.y;
-  const double x = (r & 1) ? -bx : bx, y = (r & 2) ? -by : by, phi = (r == 1 || r == 2) ? -Q.phi : Q.phi;
+  const bool neg = (r == 1 || r == 2);
+  const double x = (r & 1) ? -bx : bx, y = (r & 2) ? -by : by, phi = neg ? -Q.phi : Q.phi, sp = neg ? -Q.sp : Q.sp, cp = Q.cp;
   switch (fam) {
-    case 0: return rs_LSL(x, y, phi, t, u, v);
-    case 1: return rs_LSR(x, y, phi, t, u, v);
-    case 2: case 3: return rs_LRL(x, y, phi, t, u, v);
-    case 4: return rs_LRLRn(x, y, phi, t, u, v);
-    case 5: return rs_LRLRp(x, y, phi, t, u, v);
-    case 6: case 8: return rs_LRSL(x, y, phi, t, u, v);
-    case 7: case 9: return rs_LRSR(x, y, phi, t, u, v);
-    default: return rs_LRSLR(x, y, phi, t, u, v);
+    case 0: return rs_LSL(x, y, phi, sp, cp, t, u, v);
+    case 1: return rs_LSR(x, y, phi, sp, cp, t, u, v);
+    case 2: case 3: return rs_LRL(x, y, phi, sp, cp, t, u, v);
+    case 4: return rs_LRLRn(x, y, phi, sp, cp, t, u, v);
+    case 5: return rs_LRLRp(x, y, phi, sp, cp, t, u, v);
+    case 6: case 8: return rs_LRSL(x, y, phi, sp, cp, t, u, v);
+    case 7: case 9: return rs_LRSR(x, y, phi, sp, cp, t, u, v);
+    default: return rs_LRSLR(x, y, phi, sp, cp, t, u, v);
   }
 }
 
@@ -435,29 +450,35 @@ __device__ __forceinline__ int rs_arrange(int inst, double t, double u, double v
 
 // Candidate results of the 46 instances (filled in parallel), then the sequential
 // set_path / calc_optimal_path semantics (rs_curve.py:137-156, :99-110).
-struct RsCand { double t, u, v; };
+struct RsCand { double t, u, v, L; };   // L = sum(|lengths|) of the arranged word (rs_curve.py:148)
 
 struct RsBest { int ok; int degenerate; int n; int ct; double len[5]; double L; /* normalised */ };
 
-__device__ __forceinline__ int rs_group_start(int inst) {
-  // first instance that can share a ctype with `inst` (same family pair)
-  if (inst < 2) return inst;
-  const int fam = (inst - 2) >> 2;
-  const int gfam = (fam == 3) ? 2 : (fam == 5) ? 4 : fam;
-  return 2 + 4 * gfam;
+// instances that can share a ctype form 11 groups (same family pair), in instance order
+__device__ __constant__ int8_t rs_grp_begin[12] = {0, 1, 2, 6, 10, 18, 26, 30, 34, 38, 42, 46};
+#define RS_NGROUP 11
+struct RsGroupBest { int inst; int degenerate; double Lm; };    // inst < 0: nothing retained
+
+// L of one arranged candidate (computed where the candidate is evaluated, in parallel)
+__device__ __forceinline__ double rs_cand_L(int inst, const RsCand &c, int xy_np, int phi_np) {
+  double l[5], a[5]; int ct; unsigned mask;
+  const int n = rs_arrange(inst, c.t, c.u, c.v, xy_np, phi_np, l, ct, mask);
+  for (int i = 0; i < n; ++i) a[i] = fabs(l[i]);
+  return py_sum(a, n, mask);
 }
 
-__device__ __forceinline__ void rs_select(const RsCand *cand, unsigned long long valid, int xy_np, int phi_np,
-                                          double maxc, RsBest &best) {
+// set_path + calc_optimal_path restricted to one group (rs_curve.py:137-156, :99-110)
+__device__ __forceinline__ void rs_select_group(const RsCand *cand, unsigned long long valid, int g, int xy_np, int phi_np,
+                                                double maxc, RsGroupBest &out) {
   unsigned long long retained = 0ull;
-  best.ok = 0; best.degenerate = 0;
-  double minL = 0.0; bool first = true;
-  for (int inst = 0; inst < RS_NINST; ++inst) {
+  out.inst = -1; out.degenerate = 0; out.Lm = 0.0;
+  const int beg = rs_grp_begin[g], end = rs_grp_begin[g + 1];
+  for (int inst = beg; inst < end; ++inst) {
     if (!((valid >> inst) & 1ull)) continue;
     double l[5]; int ct; unsigned mask;
     const int n = rs_arrange(inst, cand[inst].t, cand[inst].u, cand[inst].v, xy_np, phi_np, l, ct, mask);
     bool dup = false;
-    for (int e = rs_group_start(inst); e < inst; ++e) {
+    for (int e = beg; e < inst; ++e) {
       if (!((retained >> e) & 1ull)) continue;
       double le[5], d[5]; int cte; unsigned me;
       rs_arrange(e, cand[e].t, cand[e].u, cand[e].v, xy_np, phi_np, le, cte, me);
@@ -466,18 +487,37 @@ __device__ __forceinline__ void rs_select(const RsCand *cand, unsigned long long
       if (py_sum(d, n, mask) <= 0.01) { dup = true; break; }     // rs_curve.py:143-146
     }
     if (dup) continue;
-    double a[5];
-    for (int i = 0; i < n; ++i) a[i] = fabs(l[i]);
-    const double L = py_sum(a, n, mask);                          // rs_curve.py:148
+    const double L = cand[inst].L;
     if (L >= 1000.0) continue;                                    // MAX_LENGTH
-    if (!(L >= 0.01)) { best.degenerate = 1; continue; }          // assert (rs_curve.py:153)
+    if (!(L >= 0.01)) { out.degenerate = 1; continue; }           // assert (rs_curve.py:153)
     retained |= (1ull << inst);
     const double Lm = L / maxc;
-    if (first || Lm <= minL) {           // last <= wins (rs_curve.py:106-108)
-      first = false; minL = Lm; best.ok = 1; best.n = n; best.ct = ct; best.L = L;
-      for (int i = 0; i < n; ++i) best.len[i] = l[i];
-    }
+    if (out.inst < 0 || Lm <= out.Lm) { out.inst = inst; out.Lm = Lm; }     // last <= wins
   }
+}
+
+// combine the group winners in order (equivalent to the sequential scan over all retained words)
+__device__ __forceinline__ void rs_combine_groups(const RsGroupBest *gb, const RsCand *cand, int xy_np, int phi_np, RsBest &best) {
+  best.ok = 0; best.degenerate = 0;
+  int bi = -1; double minL = 0.0;
+  for (int g = 0; g < RS_NGROUP; ++g) {
+    best.degenerate |= gb[g].degenerate;
+    if (gb[g].inst < 0) continue;
+    if (bi < 0 || gb[g].Lm <= minL) { bi = gb[g].inst; minL = gb[g].Lm; }
+  }
+  if (bi >= 0) {
+    unsigned mask;
+    best.ok = 1; best.n = rs_arrange(bi, cand[bi].t, cand[bi].u, cand[bi].v, xy_np, phi_np, best.len, best.ct, mask);
+    best.L = cand[bi].L;
+  }
+}
+
+// single-thread selection (API kernels)
+__device__ __forceinline__ void rs_select(RsCand *cand, unsigned long long valid, int xy_np, int phi_np,
+                                          double maxc, RsBest &best) {
+  RsGroupBest gb[RS_NGROUP];
+  for (int g = 0; g < RS_NGROUP; ++g) rs_select_group(cand, valid, g, xy_np, phi_np, maxc, gb[g]);
+  rs_combine_groups(gb, cand, xy_np, phi_np, best);
 }
 
 // rs_curve.py:597-624

@@ -10,13 +10,18 @@
 #pragma once
 #include "avp_dev.cuh"
 
-#ifndef AVP_BLOCK
-#define AVP_BLOCK 64          // threads per search CTA
+#ifndef AVP_BLOCK_NARROW
+#define AVP_BLOCK_NARROW 64   // pass 1: many narrow CTAs (Dijkstra-bound, short searches)
+#endif
+#ifndef AVP_BLOCK_WIDE
+#define AVP_BLOCK_WIDE 512    // pass 2: few wide CTAs for the long tail (per-pop latency bound)
 #endif
 #ifndef AVP_SM_HEAP
 #define AVP_SM_HEAP 1024      // Dijkstra heap entries kept in shared memory (the rest spills to L2/HBM)
 #endif
-#define AVP_NWARPS (AVP_BLOCK / 32)
+#ifndef AVP_SM_OPEN
+#define AVP_SM_OPEN 1024      // open-list heap entries kept in shared memory
+#endif
 #define AVP_COURSE_CAP 1024
 #define AVP_HQ_CAP 256
 #ifndef AVP_NCHILD_MAX
@@ -27,7 +32,8 @@ struct __align__(16) Node {
   double x, y, theta, f, g, h;
   int32_t parent;
   uint8_t forward, steer_idx, in_open, in_closed;
-  int32_t pad0, pad1;
+  int32_t hpos;            // position of this node's entry in the open heap (valid while in_open)
+  int32_t pad1;
 };
 static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
 
@@ -45,7 +51,8 @@ struct KParams {
   // per-slot (persistent CTA) workspaces
   unsigned long long *dheap; int dheap_cap;
   Node *nodes; int node_cap;
-  int32_t *oheap;
+  double *oheap_f;                // open heap keys beyond the shared-memory part (node_cap per slot)
+  int32_t *oheap;                 // open heap node indices beyond the shared-memory part
   int32_t *htab; int htab_size;   // power of two
   double *course;                 // 3*AVP_COURSE_CAP doubles per slot
   int32_t *course_dir;
@@ -55,6 +62,10 @@ struct KParams {
   int32_t *pops; int cap_pops;
   int32_t *hq_log;                // n * AVP_HQ_CAP * 3, may be NULL
   int *work_counter;
+  const int32_t *work_list;       // NULL: scenarios 0..n_work-1; else the ids to process (pass 2)
+  int n_work;
+  int pop_budget;                 // pass 1: a scenario still searching after this many pops ends AVP_PENDING
+  long long *prof;                // n * 8 SM-cycle accumulators per scenario (thread 0): phases of the main loop, may be NULL
   int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
   long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY
 };
@@ -192,7 +203,7 @@ __device__ __forceinline__ void rs_length_warp(const double q0[3], const double 
   for (int base = 0; base < RS_NINST; base += 32) {
     const int inst = base + lane;
     bool ok = false;
-    if (inst < RS_NINST) { double t, u, v; ok = rs_eval_instance(inst, Q, t, u, v); if (ok) { cand[inst].t = t; cand[inst].u = u; cand[inst].v = v; } }
+    if (inst < RS_NINST) { double t, u, v; ok = rs_eval_instance(inst, Q, t, u, v); if (ok) { cand[inst].t = t; cand[inst].u = u; cand[inst].v = v; cand[inst].L = rs_cand_L(inst, cand[inst], xy_np, phi_np); } }
     valid |= (unsigned long long)__ballot_sync(AVP_FULL_MASK, ok) << base;
   }
   __syncwarp();
@@ -388,7 +399,9 @@ __device__ __noinline__ int dij_compute_path(DijCtx &D, double node_x, double no
 }
 
 // ------------------------------------------------------------------------------------------
-// hybrid A* containers (per slot, global memory)
+// hybrid A* containers (per slot)
+
+#define AVP_PENDING 7   // internal: pass 1 ran out of its pop budget; pass 2 re-plans the scenario
 
 __device__ __forceinline__ unsigned long long pose_hash(double x, double y, double t) {
   const unsigned long long a = (unsigned long long)__double_as_longlong(x + 0.0), b = (unsigned long long)__double_as_longlong(y + 0.0),
@@ -408,33 +421,52 @@ __device__ __forceinline__ int htab_find(const int32_t *htab, int mask, const No
   }
   return -1;
 }
+// concurrent insert (distinct poses): claim the first empty slot of the probe sequence
 __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node *nodes, int idx) {
   const Node &n = nodes[idx];
   unsigned long long p = pose_hash(n.x, n.y, n.theta);
-  for (int probes = 0; probes <= mask; ++probes, ++p) if (htab[p & mask] < 0) { htab[p & mask] = idx; return; }
+  for (int probes = 0; probes <= mask; ++probes, ++p)
+    if (atomicCAS((int *)&htab[p & mask], -1, idx) == -1) return;
 }
-// open_list: heapq of node indices ordered by Node.__lt__ (f only, hybrid_a_star.py:61-68)
-__device__ __forceinline__ void open_siftdown(int32_t *heap, const Node *nodes, int start, int pos) {
-  const int item = heap[pos]; const double fi = nodes[item].f;
+
+// open_list: CPython heapq of Node objects ordered by Node.__lt__ (f only, hybrid_a_star.py:61-68).
+// Entries carry a copy of f (kept in sync on the reference's in-place updates through Node.hpos);
+// the first AVP_SM_OPEN entries live in shared memory.
+struct OpenHeap {
+  double *sf; int32_t *si;      // shared part
+  double *gf; int32_t *gi;      // global part
+  Node *nodes;
+  int n;
+};
+__device__ __forceinline__ double oh_f(const OpenHeap &H, int i) { return i < AVP_SM_OPEN ? H.sf[i] : H.gf[i - AVP_SM_OPEN]; }
+__device__ __forceinline__ int oh_i(const OpenHeap &H, int i) { return i < AVP_SM_OPEN ? H.si[i] : H.gi[i - AVP_SM_OPEN]; }
+__device__ __forceinline__ void oh_set(OpenHeap &H, int i, double f, int idx) {
+  if (i < AVP_SM_OPEN) { H.sf[i] = f; H.si[i] = idx; } else { H.gf[i - AVP_SM_OPEN] = f; H.gi[i - AVP_SM_OPEN] = idx; }
+  H.nodes[idx].hpos = i;
+}
+__device__ __forceinline__ void oh_siftdown(OpenHeap &H, int start, int pos) {      // heapq._siftdown
+  const double fi = oh_f(H, pos); const int item = oh_i(H, pos);
   while (pos > start) {
-    const int parent = (pos - 1) >> 1; const int pv = heap[parent];
-    if (fi < nodes[pv].f) { heap[pos] = pv; pos = parent; continue; }
+    const int parent = (pos - 1) >> 1; const double pf = oh_f(H, parent);
+    if (fi < pf) { oh_set(H, pos, pf, oh_i(H, parent)); pos = parent; continue; }
     break;
   }
-  heap[pos] = item;
+  oh_set(H, pos, fi, item);
 }
-__device__ __forceinline__ void open_siftup(int32_t *heap, const Node *nodes, int n, int pos) {
-  const int start = pos, item = heap[pos];
+__device__ __forceinline__ void oh_siftup(OpenHeap &H, int pos) {                   // heapq._siftup
+  const int n = H.n, start = pos;
+  const double fi = oh_f(H, pos); const int item = oh_i(H, pos);
   int child = 2 * pos + 1;
   while (child < n) {
     const int right = child + 1;
-    int cv = heap[child];
-    if (right < n) { const int rv = heap[right]; if (!(nodes[cv].f < nodes[rv].f)) { child = right; cv = rv; } }
-    heap[pos] = cv; pos = child; child = 2 * pos + 1;
+    double cf = oh_f(H, child);
+    if (right < n) { const double rf = oh_f(H, right); if (!(cf < rf)) { child = right; cf = rf; } }
+    oh_set(H, pos, cf, oh_i(H, child)); pos = child; child = 2 * pos + 1;
   }
-  heap[pos] = item;
-  open_siftdown(heap, nodes, start, pos);
+  oh_set(H, pos, fi, item);
+  oh_siftdown(H, start, pos);
 }
+__device__ __forceinline__ void oh_push(OpenHeap &H, double f, int idx) { oh_set(H, H.n, f, idx); H.n++; oh_siftdown(H, 0, H.n - 1); }
 
 // hybrid_a_star.py:243-259
 __device__ __forceinline__ double node_cost(const avp_config &c, bool gear, double theta, double father_theta, bool father_gear) {
@@ -444,22 +476,42 @@ __device__ __forceinline__ double node_cost(const avp_config &c, bool gear, doub
   return c.cost_scale * cost;
 }
 
+// successor i of a node (hybrid_a_star.py:134-151)
+__device__ __forceinline__ void child_pose(const avp_config &cfg, const Node &cn, int i, int nchild, double &x_, double &y_, double &th) {
+  const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+  const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+  const double td = speed * cfg.dt;
+  th = pi_2_pi(cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
+  x_ = cn.x + td * d_cos(th); y_ = cn.y + td * d_sin(th);
+}
+
 // ------------------------------------------------------------------------------------------
-// the search kernel: PathPlanner.a_star_plan (path_planner.py:58-110) for one scenario per CTA.
+// the search kernel: PathPlanner.a_star_plan (path_planner.py:58-110), one scenario per CTA at a
+// time; CTAs are persistent and pull scenarios from an atomic counter.
 
 enum { CTL_RUN = 0, CTL_EXIT = 1 };
 
-__global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 4)) k_search(KParams P) {
+  constexpr int NWARPS = BLOCK / 32;
   __shared__ unsigned long long s_heap[AVP_SM_HEAP];
+  __shared__ double s_of[AVP_SM_OPEN];
+  __shared__ int32_t s_oi[AVP_SM_OPEN];
   __shared__ RsCand s_cand[AVP_NCHILD_MAX + 1][RS_NINST];
   __shared__ unsigned long long s_valid[AVP_NCHILD_MAX + 1];
   __shared__ double s_cpose[AVP_NCHILD_MAX][3];
   __shared__ double s_rsL[AVP_NCHILD_MAX];
-  __shared__ int s_found[AVP_NCHILD_MAX], s_coll[AVP_NCHILD_MAX], s_need[AVP_NCHILD_MAX], s_rsok[AVP_NCHILD_MAX], s_skip[AVP_NCHILD_MAX];
-  __shared__ int s_scen, s_ctl, s_cur, s_in_radius, s_npts, s_shot_coll, s_shot_bad;
-  __shared__ int s_G, s_nclosed, s_npops, s_on, s_status, s_nhq, s_nhcalls;
+  __shared__ double s_org[AVP_MAX_RS_SEG + 1][3];
+  __shared__ RsQuery s_Q[AVP_NCHILD_MAX + 1];
+  __shared__ double s_sub[AVP_NCHILD_MAX][4][4];          // sub-step poses of the successors: x, y, cos, sin (hybrid_a_star.py:185-194)
+  __shared__ RsGroupBest s_grp[AVP_NCHILD_MAX + 1][RS_NGROUP];
+  __shared__ double s_g[AVP_NCHILD_MAX], s_oldf[AVP_NCHILD_MAX];
+  __shared__ int s_found[AVP_NCHILD_MAX], s_coll[AVP_NCHILD_MAX], s_need[AVP_NCHILD_MAX], s_rsok[AVP_NCHILD_MAX], s_skip[AVP_NCHILD_MAX], s_hv[AVP_NCHILD_MAX];
+  __shared__ int s_scen, s_ctl, s_cur, s_in_radius, s_npts, s_nplan, s_shot_coll, s_shot_bad;
+  __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls;
   __shared__ RsBest s_best;
   __shared__ DijCtx s_D;
+  __shared__ OpenHeap s_O;
 
   const avp_config &cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -467,7 +519,6 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
   const int nchild = 2 * cfg.steering_angle_num;
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
-  int32_t *oheap = P.oheap + (size_t)slot * P.node_cap;
   int32_t *htab = P.htab + (size_t)slot * P.htab_size;
   const int hmask = P.htab_size - 1;
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
@@ -476,8 +527,8 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
   for (;;) {
     if (tid == 0) s_scen = atomicAdd(P.work_counter, 1);
     __syncthreads();
-    const int sc = s_scen;
-    if (sc >= P.n_scen) break;
+    if (s_scen >= P.n_work) break;
+    const int sc = P.work_list ? P.work_list[s_scen] : s_scen;
     const ScenDev &S = P.scen[sc];
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
@@ -487,19 +538,23 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
     int32_t *hql = P.hq_log ? P.hq_log + (size_t)sc * AVP_HQ_CAP * 3 : nullptr;
     int *dbg = P.dbg ? P.dbg + (size_t)sc * 8 : nullptr;
     const long long t_start = clock64();
-    if (dbg && tid == 0) { dbg[0] = 1; dbg[1] = 0; }
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
+#define AVP_TICK(k) do { if (tid == 0) { const long long t_ = clock64(); pc[k] += t_ - tp; tp = t_; } } while (0)
 
     // ---- per-scenario initialisation (all threads)
-    for (int i = tid; i < S.n_ids; i += AVP_BLOCK) { hval[i] = -1; ost[i] = -1; }
-    for (int i = tid; i < P.htab_size; i += AVP_BLOCK) htab[i] = -1;
+    for (int i = tid; i < S.n_ids; i += BLOCK) { hval[i] = -1; ost[i] = -1; }
+    for (int i = tid; i < P.htab_size; i += BLOCK) htab[i] = -1;
     if (tid == 0) {
       s_D.S = &S; s_D.cost = P.cost + S.cost_off; s_D.hval = hval; s_D.ost = ost;
       s_D.gx = P.gx + S.id_off; s_D.gy = P.gy + S.id_off;
       s_D.sheap = s_heap; s_D.gheap = P.dheap + (size_t)slot * P.dheap_cap; s_D.gcap = P.dheap_cap;
       s_D.hn = 0; s_D.closed_len = 0; s_D.status = 0;
-      s_G = 0; s_nclosed = 0; s_npops = 0; s_on = 0; s_nhq = 0; s_nhcalls = 0;
+      s_O.sf = s_of; s_O.si = s_oi; s_O.gf = P.oheap_f + (size_t)slot * P.node_cap; s_O.gi = P.oheap + (size_t)slot * P.node_cap;
+      s_O.nodes = nodes; s_O.n = 0;
+      s_G = 0; s_nclosed = 0; s_npops = 0; s_nhq = 0; s_nhcalls = 0;
       s_status = S.raster_error ? AVP_RASTER_AMBIGUOUS : 0;
       s_cur = -1; s_in_radius = 0; s_shot_coll = 0; s_npts = 0; s_best.ok = 0;
+      if (dbg) { dbg[0] = 1; dbg[1] = 0; }
     }
     __syncthreads();
 
@@ -512,221 +567,304 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
         s_nhq++;
         if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
         Node r; r.x = S.pose[0]; r.y = S.pose[1]; r.theta = pi_2_pi(S.pose[2]); r.f = 0; r.g = 0; r.h = 0; r.parent = -1;
-        r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.pad0 = 0; r.pad1 = 0;
+        r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0; r.pad1 = 0;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
-        oheap[0] = 0; s_on = 1;
+        oh_push(s_O, 0.0, 0);
       }
     }
 
     // ---- main loop (path_planner.py:68-98)
     bool reached = false;
-    if (dbg && tid == 0) dbg[0] = 2;
+    AVP_TICK(0);                               // init + eager Dijkstra
     for (;;) {
       __syncthreads();
+      AVP_TICK(6);                             // commit (phase 5) of the previous iteration
       if (tid == 0) {
-        if (dbg) { dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_on; }
+        if (dbg) { dbg[0] = 2; dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_O.n; }
         if (P.watchdog_cycles > 0 && clock64() - t_start > P.watchdog_cycles && s_status == 0) s_status = AVP_CAPACITY;
-        if (s_status != 0 || s_on == 0) s_ctl = CTL_EXIT;
+        if (s_status != 0 || s_O.n == 0) s_ctl = CTL_EXIT;
         else if (s_npops >= cfg.max_pops) { s_status = AVP_CAPACITY; s_ctl = CTL_EXIT; }
+        else if (s_npops >= P.pop_budget) { s_status = AVP_PENDING; s_ctl = CTL_EXIT; }
         else {
-          // open_list.get() == heapq.heappop
-          const int last = oheap[--s_on]; int ret = last;
-          if (s_on) { ret = oheap[0]; oheap[0] = last; open_siftup(oheap, nodes, s_on, 0); }
+          const int ret = s_oi[0];                     // open_list.get(): the root is the next node
           s_cur = ret;
           if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
           s_npops++;
           const Node &cn = nodes[ret];
-          const double distance = sqrt(d_pow2(cn.x - goal[0]) + d_pow2(cn.y - goal[1]));   // hybrid_a_star.py:308-309 (** 2 == libm pow)
+          const double distance = sqrt(d_pow2(cn.x - goal[0]) + d_pow2(cn.y - goal[1]));   // hybrid_a_star.py:308-309
           s_in_radius = distance < cfg.flag_radius;
-          s_shot_coll = 0; s_shot_bad = 0; s_npts = 0; s_best.ok = 0;
+          s_shot_coll = 0; s_shot_bad = 0; s_npts = 0; s_nplan = 0; s_best.ok = 0;
           s_ctl = CTL_RUN;
         }
         for (int i = 0; i <= nchild; ++i) s_valid[i] = 0ull;
       }
       __syncthreads();
       if (s_ctl == CTL_EXIT) break;
-      if (dbg && tid == 0) dbg[0] = 3;
+      AVP_TICK(1);                             // loop top
       const int cur = s_cur;
       const Node cn = nodes[cur];
       const int phi_np = cur != 0;           // root theta is a Python float (see oracle generate_path)
 
-      // phase 1: rs word instances of the goal shot; successor poses + closed/open lookups
-      if (s_in_radius) {
-        const double q0[3] = {cn.x, cn.y, cn.theta};
-        RsQuery Q; rs_query(q0, goal, maxc, Q);
-        for (int inst = tid; inst < RS_NINST; inst += AVP_BLOCK) {
-          double t, u, v;
-          if (rs_eval_instance(inst, Q, t, u, v)) { s_cand[nchild][inst].t = t; s_cand[nchild][inst].u = u; s_cand[nchild][inst].v = v; atomicOr(&s_valid[nchild], 1ull << inst); }
-        }
-      }
-      for (int i = tid; i < nchild; i += AVP_BLOCK) {            // hybrid_a_star.py:134-165
-        const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-        const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-        const double td = speed * cfg.dt;
-        double th = cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt;
-        th = pi_2_pi(th);
-        const double x_ = cn.x + td * d_cos(th), y_ = cn.y + td * d_sin(th);
-        s_cpose[i][0] = x_; s_cpose[i][1] = y_; s_cpose[i][2] = th;
-        const int found = htab_find(htab, hmask, nodes, x_, y_, th);
-        const bool in_closed = found >= 0 && nodes[found].in_closed;
-        const bool oob = (s_nclosed > 0) && (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
-        s_found[i] = found; s_skip[i] = (in_closed || oob) ? 1 : 0; s_coll[i] = 0; s_need[i] = 0; s_rsok[i] = 0;
-      }
-      __syncthreads();
-
-      if (dbg && tid == 0) dbg[0] = 4;
-      // phase 2: thread 0 selects the shot word and lays out its course; meanwhile the other
-      // lanes/warps collision-check the sub-steps of new successors (hybrid_a_star.py:185-204)
-      if (tid == 0 && s_in_radius) {
-        RsBest b; rs_select(s_cand[nchild], s_valid[nchild], 1, phi_np, maxc, b);
-        if (!b.ok || b.degenerate) s_shot_bad = 1;
-        else {
-          const double q0[3] = {cn.x, cn.y, cn.theta};
-          const int np_ = rs_course(b, maxc, 0.5, q0, AVP_COURSE_CAP, CX, CY, CYAW, CDIR);
-          if (np_ < 0) s_shot_bad = 2; else s_npts = np_;
-          s_best = b;
-        }
+      // phase 0: successor poses and the normalised rs queries (threads 32.. so that thread 0 can
+      //          finish heapq.heappop meanwhile: move the last entry to the root, sift)
+      if (tid == 0) {
+        const int last = s_O.n - 1;
+        const double lf = oh_f(s_O, last); const int li = oh_i(s_O, last);
+        s_O.n = last;
+        if (last > 0) { oh_set(s_O, 0, lf, li); oh_siftup(s_O, 0); }
       }
       {
-        const int w0 = (AVP_NWARPS > 1) ? warp - 1 : 0, nw = (AVP_NWARPS > 1) ? AVP_NWARPS - 1 : 1;
-        if (AVP_NWARPS == 1 || warp >= 1) {
-          for (int i = w0; i < nchild; i += nw) {
-            if (s_skip[i] || s_found[i] >= 0) continue;
+        const int t0 = (BLOCK >= 64) ? 32 : 0;       // keep thread 0's warp free for the heap
+        const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
+        for (int item = tid - t0; item >= 0 && item < (nchild + 1) + nchild * nsub; item += BLOCK - t0) {
+          if (item <= nchild) {
+            const int c = item;
+            double q0[3];
+            if (c == nchild) { q0[0] = cn.x; q0[1] = cn.y; q0[2] = cn.theta; }
+            else { child_pose(cfg, cn, c, nchild, q0[0], q0[1], q0[2]); s_cpose[c][0] = q0[0]; s_cpose[c][1] = q0[1]; s_cpose[c][2] = q0[2]; }
+            if (c < nchild || s_in_radius) rs_query(q0, goal, maxc, s_Q[c]);
+          } else {
+            const int i = (item - nchild - 1) / nsub, k = (item - nchild - 1) % nsub;
             const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
             const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-            int coll = 0;
-            for (int k = 0; k < cfg.n_substeps; ++k) {
-              const double td_i = speed * cfg.ddt * (k + 1);
-              double th_i = cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1);
-              th_i = pi_2_pi(th_i);
-              const double x_i = cn.x + td_i * d_cos(th_i), y_i = cn.y + td_i * d_sin(th_i);
-              if (check_pose_warp(cfg, S, cells, col_start, x_i, y_i, th_i)) { coll = 1; break; }
-            }
-            if (lane == 0) s_coll[i] = coll;
+            const double td_i = speed * cfg.ddt * (k + 1);
+            const double th_i = pi_2_pi(cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+            const double cs = d_cos(th_i), sn = d_sin(th_i);
+            s_sub[i][k][0] = cn.x + td_i * cs; s_sub[i][k][1] = cn.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
           }
         }
       }
       __syncthreads();
+      AVP_TICK(2);                             // heappop + poses/queries
+      // phase 1a: the warps take the successors: closed/open lookup, sub-step collision checks (hybrid_a_star.py:154-204)
+      for (int i = warp; i < nchild; i += NWARPS) {
+        const double x_ = s_cpose[i][0], y_ = s_cpose[i][1], th = s_cpose[i][2];
+        int found = -1, skip = 0;
+        if (lane == 0) {
+          found = htab_find(htab, hmask, nodes, x_, y_, th);
+          const bool in_closed = found >= 0 && nodes[found].in_closed;
+          const bool oob = (s_nclosed > 0) && (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
+          skip = (in_closed || oob) ? 1 : 0;
+          s_found[i] = found; s_skip[i] = skip; s_rsok[i] = 0; s_hv[i] = -1;
+        }
+        found = __shfl_sync(AVP_FULL_MASK, found, 0); skip = __shfl_sync(AVP_FULL_MASK, skip, 0);
+        int coll = 0;
+        if (!skip && found < 0) {
+          for (int k = 0; k < cfg.n_substeps; ++k) {
+            bool hit;
+            if (k < 4) hit = check_pose_cs_warp(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3]);
+            else {
+              const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+              const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+              const double td_i = speed * cfg.ddt * (k + 1);
+              const double th_i = pi_2_pi(cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+              hit = check_pose_warp(cfg, S, cells, col_start, cn.x + td_i * d_cos(th_i), cn.y + td_i * d_sin(th_i), th_i);
+            }
+            if (hit) { coll = 1; break; }
+          }
+        }
+        if (lane == 0) { s_coll[i] = coll; s_need[i] = (!skip) && ((found < 0 && !coll) || (found >= 0)); }
+      }
+      // phase 1b: rs word instances: row nchild = the goal shot of the popped node, rows 0..nchild-1 = successors
+      // (speculative for successors that turn out skipped / colliding: it needs no barrier after 1a)
+      for (int item = tid; item < (nchild + 1) * RS_NINST; item += BLOCK) {
+        const int row = item / RS_NINST, inst = item - row * RS_NINST;
+        if (row == nchild && !s_in_radius) continue;
+        double t, u, v;
+        if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
+          RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
+          c.L = rs_cand_L(inst, c, 1, (row == nchild) ? phi_np : 1);
+          s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
+        }
+      }
+      __syncthreads();
+      AVP_TICK(3);                             // lookups, collision checks, rs instances
+
+      // phase 2a: set_path de-duplication + minimum per (row, ctype group) in parallel
+      for (int item = tid; item < (nchild + 1) * RS_NGROUP; item += BLOCK) {
+        const int row = item / RS_NGROUP, g = item - row * RS_NGROUP;
+        if (row == nchild ? !s_in_radius : !s_need[row]) continue;
+        rs_select_group(s_cand[row], s_valid[row], g, 1, (row == nchild) ? phi_np : 1, maxc, s_grp[row][g]);
+      }
+      __syncthreads();
+      // phase 2b: threads 0..nchild-1 combine the successors' groups (calc_optimal_path); another thread
+      //           combines the shot's, then lays out its segment origins and course plan
+      if (tid < nchild) {
+        if (s_need[tid]) {
+          RsBest b; rs_combine_groups(s_grp[tid], s_cand[tid], 1, 1, b);
+          s_rsok[tid] = (b.ok && !b.degenerate) ? 1 : 0;
+          s_rsL[tid] = b.ok ? b.L / maxc : 0.0;
+        }
+      }
+      const int shot_tid = (BLOCK > 32) ? 32 : nchild;
+      if (tid == shot_tid && s_in_radius) {
+        RsBest b; rs_combine_groups(s_grp[nchild], s_cand[nchild], 1, phi_np, b);
+        if (!b.ok || b.degenerate) s_shot_bad = 1;
+        else {
+          // generate_local_course (rs_curve.py:537-594), sequential part: which (segment, arc length)
+          // writes each point index last, and the segment origins
+          const double step = 0.5 * maxc;
+          const int point_num = (int)(b.L / step) + b.n + 3;
+          if (point_num > AVP_COURSE_CAP) s_shot_bad = 2;
+          else {
+            const char *mode = rs_ct_names[b.ct];
+            s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
+            int ind = 1; double d, pd, ll = 0.0;
+            CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
+            for (int i = 0; i < b.n; ++i) {
+              const double l = b.len[i];
+              d = (l > 0.0) ? step : -step;
+              ind -= 1;
+              if (i >= 1 && (b.len[i - 1] * b.len[i]) > 0) pd = -d - ll; else pd = d - ll;
+              while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
+              if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
+              ll = l - pd - d;
+              ind += 1; CYAW[ind] = l; CDIR[ind] = i;
+              int dir;
+              rs_interpolate(l, mode[i], maxc, s_org[i][0], s_org[i][1], s_org[i][2], s_org[i + 1][0], s_org[i + 1][1], s_org[i + 1][2], dir);
+              if (mode[i] == 'S') s_org[i + 1][2] = s_org[i][2];
+            }
+            s_nplan = ind + 1;
+            s_best = b;
+          }
+        }
+      }
+      __syncthreads();
+      AVP_TICK(4);                             // selection + course plan
       if (s_shot_bad) { if (tid == 0) s_status = (s_shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; continue; }
 
-      if (dbg && tid == 0) dbg[0] = 5;
-      // phase 3: collision check of the shot's course (hybrid_a_star.py:334-347)
       if (s_in_radius) {
+        // phase 3a: course points in parallel (rs_curve.py:597-624), local frame
+        const int nplan = s_nplan;
+        const char *mode = rs_ct_names[s_best.ct];
+        for (int j = tid; j < nplan; j += BLOCK) {
+          if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
+          const int seg = CDIR[j]; const double l = CYAW[j];
+          double px, py, pyaw = 0.0; int dir;
+          rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
+          if (mode[seg] == 'S') pyaw = s_org[seg][2];
+          CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
+        }
+        __syncthreads();
+        // phase 3b: drop trailing points whose local x is 0.0 (rs_curve.py:588-592), global transform (:124-130)
+        if (tid == 0) { int n = nplan; while (n > 0 && CX[n - 1] == 0.0) --n; s_npts = n; }
+        __syncthreads();
         const int npts = s_npts;
-        for (int i = warp; i < npts; i += AVP_NWARPS) {
+        const double cm = d_cos(-cn.theta), sm = d_sin(-cn.theta);
+        for (int j = tid; j < npts; j += BLOCK) {
+          const double ix = CX[j], iy = CY[j];
+          CX[j] = cm * ix + sm * iy + cn.x; CY[j] = -sm * ix + cm * iy + cn.y;
+          CYAW[j] = pi_2_pi(CYAW[j] + cn.theta);
+        }
+        __syncthreads();
+        // phase 3c: collision check of the course (hybrid_a_star.py:334-347)
+        for (int i = warp; i < npts; i += NWARPS) {
           const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
           if (stop) break;
           if (check_pose_warp(cfg, S, cells, col_start, CX[i], CY[i], pi_2_pi(CYAW[i]))) { if (lane == 0) s_shot_coll = 1; }
         }
+        __syncthreads();
+        if (!s_shot_coll) { reached = true; break; }                 // path_planner.py:86-88
       }
-      __syncthreads();
-      if (s_in_radius && !s_shot_coll) { reached = true; break; }     // path_planner.py:86-88
 
-      if (dbg && tid == 0) dbg[0] = 6;
-      // phase 4: rs lengths of the successors that will be scored (hybrid_a_star.py:286-294)
-      for (int i = tid; i < nchild; i += AVP_BLOCK) {
-        const int f = s_found[i];
-        s_need[i] = (!s_skip[i]) && ((f < 0 && !s_coll[i]) || (f >= 0));
+      AVP_TICK(5);                             // course points + shot collision check
+      // phase 4: commit preparation in parallel: node records, exact-pose table, g values, h-table prefetch
+      if (tid < nchild && !s_skip[tid]) {
+        const int i = tid, found = s_found[i];
+        const bool fwd = i < nchild / 2.0;
+        if (found < 0) {
+          const int child = s_G + i + 1;
+          if (child >= P.node_cap) s_status = AVP_CAPACITY;
+          else {
+            Node n; n.x = s_cpose[i][0]; n.y = s_cpose[i][1]; n.theta = s_cpose[i][2]; n.parent = cur;
+            n.g = s_coll[i] ? 0.0 : node_cost(cfg, fwd, n.theta, cn.theta, cn.forward != 0);    // :206-209
+            n.f = 0; n.h = 0;
+            n.forward = fwd ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); n.in_open = 0;
+            n.in_closed = s_coll[i] ? 1 : 0; n.hpos = -1; n.pad1 = 0;
+            nodes[child] = n;
+            s_g[i] = n.g;
+            __threadfence_block();
+            htab_insert(htab, hmask, nodes, child);
+          }
+        } else {
+          const Node &n = nodes[found];                                                      // :219-222
+          s_g[i] = node_cost(cfg, n.forward != 0, n.theta, cn.theta, cn.forward != 0);
+          s_oldf[i] = n.f;
+        }
+        if (s_need[i]) {
+          if (!s_rsok[i]) s_status = AVP_RS_DEGENERATE;
+          const long long id = map_index(S, s_cpose[i][0], s_cpose[i][1]);                 // calc_node_heuristic (:261-283)
+          s_hv[i] = (id >= 0 && id < S.n_ids) ? hval[id] : -1;
+        }
       }
       __syncthreads();
-      for (int item = tid; item < nchild * RS_NINST; item += AVP_BLOCK) {
-        const int i = item / RS_NINST, inst = item - i * RS_NINST;
-        if (!s_need[i]) continue;
-        const double q0[3] = {s_cpose[i][0], s_cpose[i][1], s_cpose[i][2]};
-        RsQuery Q; rs_query(q0, goal, maxc, Q);
-        double t, u, v;
-        if (rs_eval_instance(inst, Q, t, u, v)) { s_cand[i][inst].t = t; s_cand[i][inst].u = u; s_cand[i][inst].v = v; atomicOr(&s_valid[i], 1ull << inst); }
-      }
-      __syncthreads();
-      for (int i = tid; i < nchild; i += AVP_BLOCK) {
-        if (!s_need[i]) continue;
-        RsBest b; rs_select(s_cand[i], s_valid[i], 1, 1, maxc, b);
-        s_rsok[i] = (b.ok && !b.degenerate) ? 1 : 0;
-        s_rsL[i] = b.ok ? b.L / maxc : 0.0;
-      }
-      __syncthreads();
+      AVP_TICK(7);                             // commit preparation
 
-      if (dbg && tid == 0) dbg[0] = 7;
-      // phase 5: sequential commit in slot order by warp 0 (hybrid_a_star.py:154-239)
-      if (warp == 0) {
-        for (int i = 0; i < nchild; ++i) {
-          if (s_skip[i]) continue;
-          if (__shfl_sync(AVP_FULL_MASK, s_status, 0)) break;
-          const int found = s_found[i];
-          const double x_ = s_cpose[i][0], y_ = s_cpose[i][1], th = s_cpose[i][2];
-          const bool fwd = i < nchild / 2.0;
-          int child = found, miss = 0; int hv = -1;
+      // phase 5: sequential commit in slot order (hybrid_a_star.py:154-239).  Lane 0 of warp 0 runs
+      // ahead over the successors whose h value is already in the table; a miss resumes the
+      // Dijkstra search, which is warp-collective.
+      if (warp == 0 && s_status == 0) {
+        int i = 0, n_miss = 0;
+        for (;;) {
+          int stop = nchild;
           if (lane == 0) {
-            if (found < 0) {
-              child = s_G + i + 1;
-              if (child >= P.node_cap) { s_status = AVP_CAPACITY; }
-              else {
-                Node n; n.x = x_; n.y = y_; n.theta = th; n.f = 0; n.g = 0; n.h = 0; n.parent = cur;
-                n.forward = fwd ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); n.in_open = 0;
-                n.in_closed = s_coll[i] ? 1 : 0; n.pad0 = 0; n.pad1 = 0;
-                nodes[child] = n;
-                htab_insert(htab, hmask, nodes, child);
-                if (s_coll[i]) s_nclosed++;
-              }
-            }
-            if (!s_status && !(found < 0 && s_coll[i])) {
-              if (!s_rsok[i]) s_status = AVP_RS_DEGENERATE;
-              else {
-                s_nhcalls++;
-                const long long id = map_index(S, x_, y_);               // calc_node_heuristic (:261-283)
+            for (; i < nchild; ++i) {
+              if (s_skip[i]) continue;
+              if (s_found[i] < 0 && s_coll[i]) { s_nclosed++; continue; }
+              int hv = s_hv[i];
+              if (n_miss > 0) {                    // a Dijkstra resume since the prefetch: re-read the table
+                const long long id = map_index(S, s_cpose[i][0], s_cpose[i][1]);
                 hv = (id >= 0 && id < S.n_ids) ? hval[id] : -1;
-                miss = hv < 0;
+              }
+              if (hv < 0) break;                   // miss: needs the warp
+              s_nhcalls++;
+              const double h1 = hv / 100.0, h2 = s_rsL[i];
+              const double h = (h2 > h1) ? h2 : h1;                       // max(h_value_1, h_value_2) (:294-296)
+              const int found = s_found[i];
+              if (found < 0) {                                            // :206-216
+                const int child = s_G + i + 1;
+                Node &n = nodes[child];
+                const double f = s_g[i] + h;
+                n.h = h; n.f = f; n.in_open = 1;
+                oh_push(s_O, f, child);
+              } else {                                                    // :219-230 (in place, no re-heapify)
+                const double new_f = h + s_g[i];
+                if (new_f < s_oldf[i]) {
+                  Node &n = nodes[found];
+                  n.f = new_f; n.g = s_g[i]; n.h = h; n.parent = cur; n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num);
+                  if (n.hpos < AVP_SM_OPEN) s_of[n.hpos] = new_f; else s_O.gf[n.hpos - AVP_SM_OPEN] = new_f;
+                }
               }
             }
+            stop = i;
           }
-          __syncwarp();
-          const int st = __shfl_sync(AVP_FULL_MASK, s_status, 0);
-          if (st) break;
-          if (found < 0 && s_coll[i]) continue;
-          miss = __shfl_sync(AVP_FULL_MASK, miss, 0);
-          if (miss) {
-            long long term;
-            const int d = dij_compute_path(s_D, x_, y_, &term);
-            if (lane == 0) {
-              if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
-              s_nhq++;
-              if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
-              hv = d;
-            }
-            __syncwarp();
-            if (__shfl_sync(AVP_FULL_MASK, s_status, 0)) break;
-          }
+          stop = __shfl_sync(AVP_FULL_MASK, stop, 0);
+          if (stop >= nchild) break;
+          // heuristic miss for successor `stop`: Dijkstra.compute_path resumes (compute_h.py:198-214)
+          long long term;
+          const int d = dij_compute_path(s_D, s_cpose[stop][0], s_cpose[stop][1], &term);
+          ++n_miss;
           if (lane == 0) {
-            const double h1 = hv / 100.0, h2 = s_rsL[i];
-            const double h = (h2 > h1) ? h2 : h1;                         // max(h_value_1, h_value_2) (:294-296)
-            child = (found < 0) ? s_G + i + 1 : found;
-            Node &n = nodes[child];
-            if (found < 0) {                                              // :206-216
-              n.g = node_cost(cfg, fwd, th, cn.theta, cn.forward != 0);
-              n.h = h; n.f = n.g + n.h;
-              n.in_open = 1;
-              oheap[s_on++] = child; open_siftdown(oheap, nodes, 0, s_on - 1);
-            } else {                                                      // :219-230 (in-place, no re-heapify)
-              const double new_g = node_cost(cfg, n.forward != 0, n.theta, cn.theta, cn.forward != 0);
-              const double new_f = h + new_g;
-              if (new_f < n.f) { n.f = new_f; n.g = new_g; n.h = h; n.parent = cur; n.forward = fwd ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); }
-            }
+            if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
+            s_nhq++;
+            if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
           }
           __syncwarp();
+          if (__shfl_sync(AVP_FULL_MASK, s_status, 0)) break;
+          // the target cell is in the table now: lane 0 continues with successor `stop`
         }
         if (lane == 0 && !s_status) { nodes[cur].in_closed = 1; nodes[cur].in_open = 0; s_nclosed++; s_G += nchild; }   // :235-239
       }
     }
     __syncthreads();
 
-    if (dbg && tid == 0) dbg[0] = 8;
     // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
     if (tid == 0) {
       avp_plan_summary &R = P.sums[sc];
       int status = s_status;
       if (!status && !reached) status = (s_in_radius && s_best.ok) ? AVP_OPEN_EXHAUSTED_RS : AVP_OPEN_EXHAUSTED;
-      R.status = status; R.n_pops = s_npops; R.global_index = s_G; R.n_closed = s_nclosed; R.n_open = s_on;
+      R.status = status; R.n_pops = s_npops; R.global_index = s_G; R.n_closed = s_nclosed; R.n_open = s_O.n;
       R.last_index = s_cur; R.n_hq = s_nhq; R.h_closed = s_D.closed_len; R.nx = S.nx; R.ny = S.ny; R.n_obs = S.n_obs;
       R.n_hcalls = s_nhcalls; R.pitch[0] = S.dx; R.pitch[1] = S.dy;
       for (int i = 0; i < 4; ++i) R.boundary[i] = S.b[i];
@@ -737,7 +875,6 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
       if (status == AVP_OK || status == AVP_OPEN_EXHAUSTED_RS) {
         double *fp = P.paths + (size_t)sc * P.cap_path * 3;
         int np_ = 0;
-        // parent walk; the chain is emitted root-first, so first measure the depth
         int depth = 0; for (int k = s_cur; k != 0; k = nodes[k].parent) ++depth;
         auto push = [&](double px, double py, double pt) { if (np_ < P.cap_path) { fp[3 * np_] = px; fp[3 * np_ + 1] = py; fp[3 * np_ + 2] = pt; } ++np_; };
         push(nodes[0].x, nodes[0].y, nodes[0].theta);
@@ -747,18 +884,18 @@ __global__ void __launch_bounds__(AVP_BLOCK) k_search(KParams P) {
           for (int j = 0; j < cfg.n_substeps; ++j) {
             const double speed = c.forward ? cfg.max_v : -cfg.max_v;
             const double td_j = speed * cfg.ddt * (j + 1);
-            double th_j = par.theta + (cfg.max_v * cfg.tan_steer[c.steer_idx]) / cfg.lw * cfg.ddt * (j + 1);
-            th_j = pi_2_pi(th_j);
+            const double th_j = pi_2_pi(par.theta + (cfg.max_v * cfg.tan_steer[c.steer_idx]) / cfg.lw * cfg.ddt * (j + 1));
             push(par.x + td_j * d_cos(th_j), par.y + td_j * d_sin(th_j), th_j);
           }
         }
         R.n_astar = np_;
         for (int i = 1; i < s_npts; ++i) push(CX[i], CY[i], CYAW[i]);
-        if (dbg) dbg[0] = 9;
         R.n_final = np_; R.n_rs = s_npts; R.rs_nseg = s_best.n; R.rs_L = s_best.L / maxc;
         for (int i = 0; i < s_best.n; ++i) R.rs_lengths[i] = s_best.len[i] / maxc;
         for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = rs_ct_names[s_best.ct][i];
       }
+      if (dbg) dbg[0] = 9;
+      if (P.prof) for (int k = 0; k < 8; ++k) P.prof[(size_t)sc * 8 + k] = pc[k];
     }
     __syncthreads();
   }

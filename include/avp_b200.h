@@ -178,6 +178,9 @@ int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *
 int avp_timer_start(avp_ctx *ctx);
 int avp_timer_stop(avp_ctx *ctx, float *elapsed_ms);
 int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms);
+/* the search runs in two passes (narrow CTAs with a pop budget, then wide CTAs for the long
+ * tail): per-pass CUDA-event times; n_pass2 = scenarios re-planned by pass 2 + 100000 * (pass-2 CTA width) */
+int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_pass2, int32_t *n_pass2);
 
 /* development aids: an in-kernel watchdog (SM clock cycles per scenario, 0 = off; a scenario
  * that exceeds it ends with AVP_CAPACITY) and the per-scenario progress checkpoints
@@ -185,6 +188,8 @@ int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms);
  * AVP_HOST_TIMEOUT_S bounds the host's wait for the search kernel. */
 int avp_set_watchdog(avp_ctx *ctx, long long cycles);
 int avp_fetch_debug(avp_ctx *ctx, int32_t *out8n);
+/* per-scenario SM-cycle accumulators of the search kernel's phases (8 int64 each, see avp_api.cu) */
+int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n);
 
 #ifdef __cplusplus
 }

@@ -232,7 +232,10 @@ def test_full_size_batch_properties(device_planner, cfg):
     """BASELINE config 2 at full size (1024 scenarios): size-independent properties."""
     dp = device_planner
     base = scn.benchmark_case(1)
-    scs = scn.perturbed_set(base, 1024, seed=1)
+    cands = scn.perturbed_candidates(base, 8 * 1024, seed=1)
+    dp.load(cands)
+    a, b = dp.start_goal_collisions()
+    scs = scn.keep_collision_free(cands, a, b, 1024)
     dp.load(scs)
     res = dp.plan(cap_path=512, cap_pops=0)
     s = res.summaries
