@@ -361,7 +361,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
   P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.watchdog_cycles = ctx->watchdog_cycles;
   const char *pb = getenv("AVP_POP_BUDGET");
-  const int budget = pb ? atoi(pb) : 192;
+  const int budget = pb ? atoi(pb) : 1024;
   P.work_list = nullptr; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;

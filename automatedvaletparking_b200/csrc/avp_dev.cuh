@@ -151,16 +151,25 @@ struct VehGeom {
   double lk[4], lb[4], ls[4];   // slope, intercept, sqrt(1+k^2) of the 4 boundary lines
 };
 
+__device__ __forceinline__ double shfl_dbl(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(AVP_FULL_MASK, lo, src); hi = __shfl_sync(AVP_FULL_MASK, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+// Warp-collective: lane l < 4 computes corner l and boundary line l, the results are exchanged by
+// shuffles (the same IEEE operations as the scalar form, evaluated once instead of 32 times and
+// with a 4x shorter dependent chain).
 __device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y, double cs, double sn, VehGeom &g) {
+  const int lane = threadIdx.x & 31, l = lane & 3;
   const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
   const double lx0 = -c.lr - fr, lx1 = c.lw + c.lf + fr, ly0 = -c.lb / 2 - sd, ly1 = c.lb / 2 + sd;
-  const double locx[4] = {lx0, lx1, lx1, lx0}, locy[4] = {ly0, ly0, ly1, ly1};
+  const double locx = (l == 0 || l == 3) ? lx0 : lx1, locy = (l < 2) ? ly0 : ly1;
+  // trans_matrix.transpose().dot(local) + [x, y]; BLAS gemv row = fma(A[r][1], v1, A[r][0]*v0)
+  const double cx = __fma_rn(-sn, locy, cs * locx) + x;
+  const double cy = __fma_rn(cs, locy, sn * locx) + y;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    // trans_matrix.transpose().dot(local) + [x, y]; BLAS gemv row = fma(A[r][1], v1, A[r][0]*v0)
-    g.vb[i][0] = __fma_rn(-sn, locy[i], cs * locx[i]) + x;
-    g.vb[i][1] = __fma_rn(cs, locy[i], sn * locx[i]) + y;
-  }
+  for (int i = 0; i < 4; ++i) { g.vb[i][0] = shfl_dbl(cx, i); g.vb[i][1] = shfl_dbl(cy, i); }
   g.vb[4][0] = g.vb[0][0]; g.vb[4][1] = g.vb[0][1];
   g.x_max = g.x_min = g.vb[0][0]; g.y_max = g.y_min = g.vb[0][1];
 #pragma unroll
@@ -168,17 +177,19 @@ __device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y
     if (g.vb[i][0] > g.x_max) g.x_max = g.vb[i][0]; if (g.vb[i][0] < g.x_min) g.x_min = g.vb[i][0];
     if (g.vb[i][1] > g.y_max) g.y_max = g.vb[i][1]; if (g.vb[i][1] < g.y_min) g.y_min = g.vb[i][1];
   }
-  double d0 = g.vb[0][0] - g.vb[3][0], d1 = g.vb[0][1] - g.vb[3][1];
-  g.v_lb = sqrt(d0 * d0 + d1 * d1);                                   // collision_check.py:165-166
-  d0 = g.vb[3][0] - g.vb[2][0]; d1 = g.vb[3][1] - g.vb[2][1];
-  g.v_len = sqrt(d0 * d0 + d1 * d1);                                  // :168-169
+  // lane l: line l between corner l and corner l+1 (collision_check.py:149-155, :180-190);
+  // lanes 0/1 additionally the two side lengths (:165-169)
+  const int nxt = (lane & ~3) | ((l + 1) & 3);
+  const double p1x = cx, p1y = cy, p2x = shfl_dbl(cx, nxt), p2y = shfl_dbl(cy, nxt);
+  const double lk = (p2y - p1y) / (p2x - p1x);
+  const double lb = p1y - lk * p1x;
+  const double ls = sqrt(1 + lk * lk);
+  double d0 = (l == 0) ? g.vb[0][0] - g.vb[3][0] : g.vb[3][0] - g.vb[2][0];
+  double d1 = (l == 0) ? g.vb[0][1] - g.vb[3][1] : g.vb[3][1] - g.vb[2][1];
+  const double side = sqrt(d0 * d0 + d1 * d1);
+  g.v_lb = shfl_dbl(side, 0); g.v_len = shfl_dbl(side, 1);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {                                       // :149-155, :180-190
-    const double *p1 = g.vb[i], *p2 = g.vb[(i < 3) ? i + 1 : 0];
-    g.lk[i] = (p2[1] - p1[1]) / (p2[0] - p1[0]);
-    g.lb[i] = p1[1] - g.lk[i] * p1[0];
-    g.ls[i] = sqrt(1 + g.lk[i] * g.lk[i]);
-  }
+  for (int i = 0; i < 4; ++i) { g.lk[i] = shfl_dbl(lk, i); g.lb[i] = shfl_dbl(lb, i); g.ls[i] = shfl_dbl(ls, i); }
 }
 
 // the per-cell predicate of distance_checker.check (collision_check.py:197-238)

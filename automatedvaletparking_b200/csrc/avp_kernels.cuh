@@ -185,7 +185,7 @@ __global__ void k_fill_cells(int n_scen, const ScenDev *scen, const uint8_t *cos
 // API kernels (single-step drop-in methods and kernel-level parity tests)
 
 // one warp per pose
-__global__ void k_check_batch(avp_config cfg, const ScenDev *scen, int s, const double2 *cells, const int32_t *col_start,
+__global__ void __launch_bounds__(128) k_check_batch(avp_config cfg, const ScenDev *scen, int s, const double2 *cells, const int32_t *col_start,
                               int m, const double *poses, uint8_t *out) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= m) return;
@@ -211,7 +211,7 @@ __device__ __forceinline__ void rs_length_warp(const double q0[3], const double 
 }
 
 // one CTA, one warp per successor (hybrid_a_star.py:133-151,185-204 + rs length)
-__global__ void k_expand_pure(avp_config cfg, const ScenDev *scen, int s, const double2 *cells, const int32_t *col_start,
+__global__ void __launch_bounds__(AVP_NCHILD_MAX * 32) k_expand_pure(avp_config cfg, const ScenDev *scen, int s, const double2 *cells, const int32_t *col_start,
                               double px, double py, double pth, double *out_pose, int32_t *out_flags, double *out_rsL) {
   __shared__ RsCand cand[AVP_NCHILD_MAX][RS_NINST];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -242,7 +242,7 @@ __global__ void k_expand_pure(avp_config cfg, const ScenDev *scen, int s, const 
 }
 
 // one warp per query (rs_curve.py:99-134), selected word + its course
-__global__ void k_rs_optimal(int m, const double *q, double maxc, double step_size, int xy_np, int phi_np,
+__global__ void __launch_bounds__(128) k_rs_optimal(int m, const double *q, double maxc, double step_size, int xy_np, int phi_np,
                              double *lengths, char *ctypes, int32_t *nseg, double *L, int cap_pts,
                              double *x, double *y, double *yaw, int32_t *dir, int32_t *n_pts) {
   __shared__ RsCand cand[4][RS_NINST];
@@ -274,128 +274,149 @@ struct DijCtx {
   int hn; int closed_len; int status;
 };
 
-__device__ __forceinline__ unsigned long long hp_get(const DijCtx &D, int i) { return i < AVP_SM_HEAP ? D.sheap[i] : D.gheap[i - AVP_SM_HEAP]; }
-__device__ __forceinline__ void hp_set(DijCtx &D, int i, unsigned long long v) { if (i < AVP_SM_HEAP) D.sheap[i] = v; else D.gheap[i - AVP_SM_HEAP] = v; }
-
-// heapq._siftdown (Lib/heapq.py:207-219)
-__device__ __forceinline__ void hp_siftdown(DijCtx &D, int start, int pos) {
-  const unsigned long long item = hp_get(D, pos);
-  while (pos > start) {
-    const int parent = (pos - 1) >> 1;
-    const unsigned long long p = hp_get(D, parent);
-    if (item < p) { hp_set(D, pos, p); pos = parent; continue; }
-    break;
-  }
-  hp_set(D, pos, item);
-}
-// heapq._siftup (Lib/heapq.py:260-278)
-__device__ __forceinline__ void hp_siftup(DijCtx &D, int pos) {
-  const int n = D.hn, start = pos;
-  const unsigned long long item = hp_get(D, pos);
-  int child = 2 * pos + 1;
-  while (child < n) {
-    const int right = child + 1;
-    unsigned long long cv = hp_get(D, child);
-    if (right < n) { const unsigned long long rv = hp_get(D, right); if (!(cv < rv)) { child = right; cv = rv; } }
-    hp_set(D, pos, cv); pos = child; child = 2 * pos + 1;
-  }
-  hp_set(D, pos, item);
-  hp_siftdown(D, start, pos);
-}
-
-// compute_h.py:237-255
-__device__ __forceinline__ bool dij_is_obstacle(const ScenDev &S, const uint8_t *cm, double gx, double gy) {
-  long long xi = (long long)floor((gx - S.b[0]) / S.dx) - 1, yi = (long long)floor((gy - S.b[2]) / S.dy) - 1;
-  if (xi >= S.mx) xi = S.mx - 1; if (yi >= S.my) yi = S.my - 1;
-  if (xi < 0) xi += S.nx; if (yi < 0) yi += S.ny;           // python negative indexing
-  if (xi < 0 || xi >= S.nx || yi < 0 || yi >= S.ny) return false;
-  return cm[(size_t)xi * S.ny + yi] == 255;
-}
-
 __device__ __forceinline__ double shfl_d(double v, int src) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_sync(AVP_FULL_MASK, lo, src); hi = __shfl_sync(AVP_FULL_MASK, hi, src);
   return __hiloint2double(hi, lo);
 }
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  lo = __shfl_sync(AVP_FULL_MASK, lo, src); hi = __shfl_sync(AVP_FULL_MASK, hi, src);
+  return ((unsigned long long)hi << 32) | lo;
+}
 
-// Dijkstra.compute_path (compute_h.py:198-214); warp-collective.  Returns the popped distance
-// of the target cell, or -1 if the queue ran dry (reference: blocks forever) / capacity.
-__device__ __noinline__ int dij_compute_path(DijCtx &D, double node_x, double node_y, long long *term_out) {
+// Dijkstra.compute_path (compute_h.py:198-214); warp-collective.  Returns the popped distance of the
+// target cell, or -1 if the queue ran dry (reference: blocks forever) / capacity.
+// `sheap` must be the kernel's __shared__ heap array (the function is inlined so that the
+// compiler keeps the shared address space); the queue persists in D / sheap / D.gheap across calls.
+__device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *sheap, double node_x, double node_y, long long *term_out) {
   const ScenDev &S = *D.S;
   const int lane = threadIdx.x & 31;
+  // loop invariants in registers
+  const uint8_t *cost = D.cost; int32_t *hval = D.hval, *ost = D.ost; double *gxa = D.gx, *gya = D.gy;
+  unsigned long long *gheap = D.gheap; const int gcap = D.gcap;
+  const double b0 = S.b[0], b1 = S.b[1], b2 = S.b[2], b3 = S.b[3], dx = S.dx, dy = S.dy;
+  const int nx = S.nx, ny = S.ny, mx = S.mx, my = S.my, stride = S.stride, n_ids = S.n_ids;
+  int hn = D.hn, closed_len = D.closed_len, status = 0;
+
+#define HP_GET(i) ((i) < AVP_SM_HEAP ? sheap[(i)] : gheap[(i) - AVP_SM_HEAP])
+#define HP_SET(i, v) do { if ((i) < AVP_SM_HEAP) sheap[(i)] = (v); else gheap[(i) - AVP_SM_HEAP] = (v); } while (0)
+
   const long long term = map_index(S, node_x, node_y);
   if (term_out) *term_out = term;
   double cur_x = S.pose[3], cur_y = S.pose[4];
   int cur_dist = 0;
   const long long gid = map_index(S, cur_x, cur_y);
-  if (lane == 0) { D.closed_len++; if (gid >= 0 && gid < S.n_ids && D.hval[gid] < 0) D.hval[gid] = 0; }   // initial_map (:50-72)
+  if (lane == 0) { if (gid >= 0 && gid < n_ids && hval[gid] < 0) hval[gid] = 0; }   // initial_map (:50-72)
+  closed_len++;
   __syncwarp();
+  int result = -1;
   for (long long guard = 0;; ++guard) {
-    if (guard > 4ll * S.n_ids + 1024) { if (lane == 0) D.status = AVP_CAPACITY; __syncwarp(); return -1; }   // cannot happen: every id is pushed at most twice
+    if (guard > 4ll * n_ids + 1024) { status = AVP_CAPACITY; break; }   // cannot happen: every id is pushed at most twice
     // update_openlist (compute_h.py:84-195): the 8 neighbours evaluated by lanes 0..7
-    bool valid = false; int prio = 0, st = 0; long long nid = 0; double ngx = 0.0, ngy = 0.0;
+    int action = 0, prio = 0; int nid = 0; unsigned long long key = 0ull;
     if (lane < 8) {
       const int ddx = (lane == 0 || lane == 3 || lane == 5) ? -1 : ((lane == 2 || lane == 4 || lane == 7) ? 1 : 0);
       const int ddy = (lane < 3) ? 1 : ((lane < 5) ? 0 : -1);
-      ngx = ddx < 0 ? cur_x - S.dx : (ddx > 0 ? cur_x + S.dx : cur_x);
-      ngy = ddy < 0 ? cur_y - S.dy : (ddy > 0 ? cur_y + S.dy : cur_y);
-      if (!dij_is_obstacle(S, D.cost, ngx, ngy)) {
+      const double ngx = ddx < 0 ? cur_x - dx : (ddx > 0 ? cur_x + dx : cur_x);
+      const double ngy = ddy < 0 ? cur_y - dy : (ddy > 0 ? cur_y + dy : cur_y);
+      const long long qx = (long long)floor((ngx - b0) / dx);                 // shared by is_obstacle and convert_position_to_index
+      // is_obstacle (compute_h.py:237-255)
+      long long xi = qx - 1, yi = (long long)floor((ngy - b2) / dy) - 1;
+      if (xi >= mx) xi = mx - 1; if (yi >= my) yi = my - 1;
+      if (xi < 0) xi += nx; if (yi < 0) yi += ny;             // python negative indexing
+      bool obstacle = false;
+      if (xi >= 0 && xi < nx && yi >= 0 && yi < ny) obstacle = cost[(size_t)xi * ny + yi] == 255;
+      if (!obstacle) {
         bool ok = true;
-        if (ddx < 0 && !(ngx >= S.b[0])) ok = false; if (ddx > 0 && !(ngx <= S.b[1])) ok = false;
-        if (ddy > 0 && !(ngy <= S.b[3])) ok = false; if (ddy < 0 && !(ngy >= S.b[2])) ok = false;
+        if (ddx < 0 && !(ngx >= b0)) ok = false; if (ddx > 0 && !(ngx <= b1)) ok = false;
+        if (ddy > 0 && !(ngy <= b3)) ok = false; if (ddy < 0 && !(ngy >= b2)) ok = false;
         if (ok) {
-          nid = map_index(S, ngx, ngy);
-          if (nid >= 0 && nid < S.n_ids) { valid = true; st = D.ost[nid]; prio = cur_dist + ((ddx && ddy) ? 14 : 10); }
-        }
-      }
-    }
-    const unsigned vmask = __ballot_sync(AVP_FULL_MASK, valid) & 0xffu;
-    for (int k = 0; k < 8; ++k) {             // add_grid_to_openlist (:216-235), in the reference's order
-      if (!((vmask >> k) & 1u)) continue;
-      const int st_k = __shfl_sync(AVP_FULL_MASK, st, k), prio_k = __shfl_sync(AVP_FULL_MASK, prio, k);
-      const int nid_k = (int)__shfl_sync(AVP_FULL_MASK, (int)nid, k);
-      if (st_k == -1) {                        // first visit: heappush
-        const double x_k = shfl_d(ngx, k), y_k = shfl_d(ngy, k);
-        if (lane == 0) {
-          if (D.hn >= AVP_SM_HEAP + D.gcap) D.status = AVP_CAPACITY;
-          else {
-            hp_set(D, D.hn, ((unsigned long long)(unsigned)prio_k << 32) | (unsigned)nid_k);
-            D.hn++; hp_siftdown(D, 0, D.hn - 1);
-            D.ost[nid_k] = prio_k; D.gx[nid_k] = x_k; D.gy[nid_k] = y_k;
+          const long long id = qx + (long long)floor((b3 - ngy) / dy) * (long long)stride;   // costmap.py:319-329
+          if (id >= 0 && id < n_ids) {
+            nid = (int)id;
+            const int st = ost[nid];
+            prio = cur_dist + ((ddx && ddy) ? 14 : 10);
+            key = ((unsigned long long)(unsigned)prio << 32) | (unsigned)nid;
+            if (st == -1) {                    // first visit (add_grid_to_openlist :229-235): this lane records the Grid
+              action = 1; ost[nid] = prio; gxa[nid] = ngx; gya[nid] = ngy;
+            } else if (st >= 0 && st > prio) action = 2;      // queued with a larger distance (:222-228)
           }
         }
-      } else if (st_k >= 0 && st_k > prio_k) {  // still queued with a larger distance: overwrite IN PLACE, no re-sift (:222-228)
+      }
+    }
+    unsigned pm = __ballot_sync(AVP_FULL_MASK, action == 1) & 0xffu, dm = __ballot_sync(AVP_FULL_MASK, action == 2) & 0xffu;
+    unsigned todo = pm | dm;
+    while (todo) {                            // in the reference's neighbour order
+      const int k = __ffs(todo) - 1; todo &= todo - 1;
+      const unsigned long long key_k = shfl_u64(key, k);
+      if ((pm >> k) & 1u) {                   // heappush
+        if (lane == 0) {
+          if (hn >= AVP_SM_HEAP + gcap) status = AVP_CAPACITY;
+          else {
+            int pos = hn++;
+            while (pos > 0) {                 // heapq._siftdown
+              const int parent = (pos - 1) >> 1;
+              const unsigned long long pv = HP_GET(parent);
+              if (key_k < pv) { HP_SET(pos, pv); pos = parent; continue; }
+              break;
+            }
+            HP_SET(pos, key_k);
+          }
+        }
+      } else {                                // overwrite IN PLACE, no re-sift (:222-228)
+        const int hn_b = __shfl_sync(AVP_FULL_MASK, hn, 0);
         __syncwarp();
         int pos = 0x7fffffff;
-        for (int i = lane; i < D.hn; i += 32) if ((unsigned)hp_get(D, i) == (unsigned)nid_k) { pos = i; break; }
+        for (int i = lane; i < hn_b; i += 32) if ((unsigned)HP_GET(i) == (unsigned)key_k) { pos = i; break; }
         for (int o = 16; o > 0; o >>= 1) pos = min(pos, __shfl_xor_sync(AVP_FULL_MASK, pos, o));
-        if (lane == 0 && pos != 0x7fffffff) {
-          hp_set(D, pos, ((unsigned long long)(unsigned)prio_k << 32) | (unsigned)nid_k);
-          D.ost[nid_k] = prio_k;
-        }
+        if (lane == 0 && pos != 0x7fffffff) { HP_SET(pos, key_k); ost[(int)(unsigned)key_k] = (int)(key_k >> 32); }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    const int st_now = __shfl_sync(AVP_FULL_MASK, D.status, 0), hn_now = __shfl_sync(AVP_FULL_MASK, D.hn, 0);
-    if (st_now) return -1;
-    if (hn_now == 0) { if (lane == 0) D.status = AVP_H_UNREACHABLE; __syncwarp(); return -1; }
+    hn = __shfl_sync(AVP_FULL_MASK, hn, 0);
+    status = __shfl_sync(AVP_FULL_MASK, status, 0);
+    if (status) break;
+    if (hn == 0) { status = AVP_H_UNREACHABLE; break; }
     // update_closedlist (:74-82): heappop
     unsigned long long top = 0ull;
     if (lane == 0) {
-      top = hp_get(D, 0);
-      const unsigned long long last = hp_get(D, D.hn - 1);
-      D.hn--;
-      if (D.hn > 0) { hp_set(D, 0, last); hp_siftup(D, 0); }
-      const int id = (int)(unsigned)top, dist = (int)(top >> 32);
-      D.ost[id] = -2; D.closed_len++;
-      if (D.hval[id] < 0) D.hval[id] = dist;
+      top = sheap[0];
+      const unsigned long long item = HP_GET(hn - 1);
+      const int n = hn - 1;
+      if (n > 0) {                            // heapq._siftup
+        int pos = 0, child = 1;
+        while (child < n) {
+          const int right = child + 1;
+          unsigned long long cv = HP_GET(child);
+          if (right < n) { const unsigned long long rv = HP_GET(right); if (!(cv < rv)) { child = right; cv = rv; } }
+          HP_SET(pos, cv); pos = child; child = 2 * pos + 1;
+        }
+        while (pos > 0) {                     // heapq._siftdown(heap, 0, pos)
+          const int parent = (pos - 1) >> 1;
+          const unsigned long long pv = HP_GET(parent);
+          if (item < pv) { HP_SET(pos, pv); pos = parent; continue; }
+          break;
+        }
+        HP_SET(pos, item);
+      }
+      const int id = (int)(unsigned)top;
+      ost[id] = -2;
+      if (hval[id] < 0) hval[id] = (int)(top >> 32);
     }
-    const int cur_id = (int)__shfl_sync(AVP_FULL_MASK, (unsigned)top, 0);
-    cur_dist = (int)__shfl_sync(AVP_FULL_MASK, (unsigned)(top >> 32), 0);
+    hn -= 1; closed_len++;
+    top = shfl_u64(top, 0);
+    const int cur_id = (int)(unsigned)top;
+    cur_dist = (int)(top >> 32);
     __syncwarp();
-    if ((long long)cur_id == term) return cur_dist;
-    cur_x = D.gx[cur_id]; cur_y = D.gy[cur_id];
+    if ((long long)cur_id == term) { result = cur_dist; break; }
+    cur_x = gxa[cur_id]; cur_y = gya[cur_id];
   }
+  if (lane == 0) { D.hn = hn; D.closed_len = closed_len; if (status) D.status = status; }
+  __syncwarp();
+  return result;
+#undef HP_GET
+#undef HP_SET
 }
 
 // ------------------------------------------------------------------------------------------
@@ -431,42 +452,39 @@ __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node 
 
 // open_list: CPython heapq of Node objects ordered by Node.__lt__ (f only, hybrid_a_star.py:61-68).
 // Entries carry a copy of f (kept in sync on the reference's in-place updates through Node.hpos);
-// the first AVP_SM_OPEN entries live in shared memory.
-struct OpenHeap {
-  double *sf; int32_t *si;      // shared part
-  double *gf; int32_t *gi;      // global part
-  Node *nodes;
-  int n;
-};
-__device__ __forceinline__ double oh_f(const OpenHeap &H, int i) { return i < AVP_SM_OPEN ? H.sf[i] : H.gf[i - AVP_SM_OPEN]; }
-__device__ __forceinline__ int oh_i(const OpenHeap &H, int i) { return i < AVP_SM_OPEN ? H.si[i] : H.gi[i - AVP_SM_OPEN]; }
-__device__ __forceinline__ void oh_set(OpenHeap &H, int i, double f, int idx) {
-  if (i < AVP_SM_OPEN) { H.sf[i] = f; H.si[i] = idx; } else { H.gf[i - AVP_SM_OPEN] = f; H.gi[i - AVP_SM_OPEN] = idx; }
-  H.nodes[idx].hpos = i;
-}
-__device__ __forceinline__ void oh_siftdown(OpenHeap &H, int start, int pos) {      // heapq._siftdown
-  const double fi = oh_f(H, pos); const int item = oh_i(H, pos);
-  while (pos > start) {
-    const int parent = (pos - 1) >> 1; const double pf = oh_f(H, parent);
-    if (fi < pf) { oh_set(H, pos, pf, oh_i(H, parent)); pos = parent; continue; }
+// the first AVP_SM_OPEN entries live in shared memory.  The functions are force-inlined and take
+// the __shared__ arrays themselves so that the compiler keeps the shared address space.
+#define OH_F(i) ((i) < AVP_SM_OPEN ? sf[(i)] : gf[(i) - AVP_SM_OPEN])
+#define OH_I(i) ((i) < AVP_SM_OPEN ? si[(i)] : gi[(i) - AVP_SM_OPEN])
+#define OH_SET(i, f_, idx_) do { if ((i) < AVP_SM_OPEN) { sf[(i)] = (f_); si[(i)] = (idx_); } else { gf[(i) - AVP_SM_OPEN] = (f_); gi[(i) - AVP_SM_OPEN] = (idx_); } nodes[(idx_)].hpos = (i); } while (0)
+__device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int pos, double fi, int item) {   // heapq._siftdown(heap, 0, pos)
+  while (pos > 0) {
+    const int parent = (pos - 1) >> 1; const double pf = OH_F(parent);
+    if (fi < pf) { const int pi = OH_I(parent); OH_SET(pos, pf, pi); pos = parent; continue; }
     break;
   }
-  oh_set(H, pos, fi, item);
+  OH_SET(pos, fi, item);
 }
-__device__ __forceinline__ void oh_siftup(OpenHeap &H, int pos) {                   // heapq._siftup
-  const int n = H.n, start = pos;
-  const double fi = oh_f(H, pos); const int item = oh_i(H, pos);
-  int child = 2 * pos + 1;
-  while (child < n) {
+__device__ __forceinline__ void oh_push(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int &n, double f, int idx) {
+  const int pos = n++;
+  oh_siftdown(sf, si, gf, gi, nodes, pos, f, idx);
+}
+// heapq.heappop after the root has been read: move the last entry to the root and _siftup
+__device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int &n) {
+  const int last = n - 1;
+  const double fi = OH_F(last); const int item = OH_I(last);
+  n = last;
+  if (last == 0) return;
+  int pos = 0, child = 1;
+  while (child < last) {
     const int right = child + 1;
-    double cf = oh_f(H, child);
-    if (right < n) { const double rf = oh_f(H, right); if (!(cf < rf)) { child = right; cf = rf; } }
-    oh_set(H, pos, cf, oh_i(H, child)); pos = child; child = 2 * pos + 1;
+    double cf = OH_F(child);
+    if (right < last) { const double rf = OH_F(right); if (!(cf < rf)) { child = right; cf = rf; } }
+    const int ci = OH_I(child);
+    OH_SET(pos, cf, ci); pos = child; child = 2 * pos + 1;
   }
-  oh_set(H, pos, fi, item);
-  oh_siftdown(H, start, pos);
+  oh_siftdown(sf, si, gf, gi, nodes, pos, fi, item);
 }
-__device__ __forceinline__ void oh_push(OpenHeap &H, double f, int idx) { oh_set(H, H.n, f, idx); H.n++; oh_siftdown(H, 0, H.n - 1); }
 
 // hybrid_a_star.py:243-259
 __device__ __forceinline__ double node_cost(const avp_config &c, bool gear, double theta, double father_theta, bool father_gear) {
@@ -511,7 +529,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
   __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls;
   __shared__ RsBest s_best;
   __shared__ DijCtx s_D;
-  __shared__ OpenHeap s_O;
+  __shared__ int s_on;                     // len(open_list.queue)
 
   const avp_config &cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -520,6 +538,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
   int32_t *htab = P.htab + (size_t)slot * P.htab_size;
+  double *ogf = P.oheap_f + (size_t)slot * P.node_cap;
+  int32_t *ogi = P.oheap + (size_t)slot * P.node_cap;
   const int hmask = P.htab_size - 1;
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
   int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
@@ -549,8 +569,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       s_D.gx = P.gx + S.id_off; s_D.gy = P.gy + S.id_off;
       s_D.sheap = s_heap; s_D.gheap = P.dheap + (size_t)slot * P.dheap_cap; s_D.gcap = P.dheap_cap;
       s_D.hn = 0; s_D.closed_len = 0; s_D.status = 0;
-      s_O.sf = s_of; s_O.si = s_oi; s_O.gf = P.oheap_f + (size_t)slot * P.node_cap; s_O.gi = P.oheap + (size_t)slot * P.node_cap;
-      s_O.nodes = nodes; s_O.n = 0;
+      s_on = 0;
       s_G = 0; s_nclosed = 0; s_npops = 0; s_nhq = 0; s_nhcalls = 0;
       s_status = S.raster_error ? AVP_RASTER_AMBIGUOUS : 0;
       s_cur = -1; s_in_radius = 0; s_shot_coll = 0; s_npts = 0; s_best.ok = 0;
@@ -561,7 +580,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
     // ---- hybrid_a_star.__init__: eager Dijkstra to the start cell (hybrid_a_star.py:89-91), root node (:102-112)
     if (warp == 0 && s_status == 0) {
       long long term;
-      const int d = dij_compute_path(s_D, S.pose[0], S.pose[1], &term);
+      const int d = dij_compute_path(s_D, s_heap, S.pose[0], S.pose[1], &term);
       if (lane == 0) {
         if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
         s_nhq++;
@@ -570,7 +589,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
         r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0; r.pad1 = 0;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
-        oh_push(s_O, 0.0, 0);
+        { int n_ = s_on; oh_push(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
       }
     }
 
@@ -581,9 +600,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       __syncthreads();
       AVP_TICK(6);                             // commit (phase 5) of the previous iteration
       if (tid == 0) {
-        if (dbg) { dbg[0] = 2; dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_O.n; }
+        if (dbg) { dbg[0] = 2; dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_on; }
         if (P.watchdog_cycles > 0 && clock64() - t_start > P.watchdog_cycles && s_status == 0) s_status = AVP_CAPACITY;
-        if (s_status != 0 || s_O.n == 0) s_ctl = CTL_EXIT;
+        if (s_status != 0 || s_on == 0) s_ctl = CTL_EXIT;
         else if (s_npops >= cfg.max_pops) { s_status = AVP_CAPACITY; s_ctl = CTL_EXIT; }
         else if (s_npops >= P.pop_budget) { s_status = AVP_PENDING; s_ctl = CTL_EXIT; }
         else {
@@ -608,12 +627,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
 
       // phase 0: successor poses and the normalised rs queries (threads 32.. so that thread 0 can
       //          finish heapq.heappop meanwhile: move the last entry to the root, sift)
-      if (tid == 0) {
-        const int last = s_O.n - 1;
-        const double lf = oh_f(s_O, last); const int li = oh_i(s_O, last);
-        s_O.n = last;
-        if (last > 0) { oh_set(s_O, 0, lf, li); oh_siftup(s_O, 0); }
-      }
+      if (tid == 0) { int n_ = s_on; oh_pop_fix(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; }
       {
         const int t0 = (BLOCK >= 64) ? 32 : 0;       // keep thread 0's warp free for the heap
         const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
@@ -668,8 +682,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       }
       // phase 1b: rs word instances: row nchild = the goal shot of the popped node, rows 0..nchild-1 = successors
       // (speculative for successors that turn out skipped / colliding: it needs no barrier after 1a)
+      // item = inst * (nchild + 1) + row: the lanes of a warp evaluate the SAME word formula for different
+      // poses (instances of one family are adjacent), instead of 32 different formulas
       for (int item = tid; item < (nchild + 1) * RS_NINST; item += BLOCK) {
-        const int row = item / RS_NINST, inst = item - row * RS_NINST;
+        const int inst = item / (nchild + 1), row = item - inst * (nchild + 1);
         if (row == nchild && !s_in_radius) continue;
         double t, u, v;
         if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
@@ -683,7 +699,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
 
       // phase 2a: set_path de-duplication + minimum per (row, ctype group) in parallel
       for (int item = tid; item < (nchild + 1) * RS_NGROUP; item += BLOCK) {
-        const int row = item / RS_NGROUP, g = item - row * RS_NGROUP;
+        const int g = item / (nchild + 1), row = item - g * (nchild + 1);       // group-major: same code path per warp
         if (row == nchild ? !s_in_radius : !s_need[row]) continue;
         rs_select_group(s_cand[row], s_valid[row], g, 1, (row == nchild) ? phi_np : 1, maxc, s_grp[row][g]);
       }
@@ -806,6 +822,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       // Dijkstra search, which is warp-collective.
       if (warp == 0 && s_status == 0) {
         int i = 0, n_miss = 0;
+        int on = s_on;                            // lane 0's register copy of the heap size
         for (;;) {
           int stop = nchild;
           if (lane == 0) {
@@ -827,13 +844,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
                 Node &n = nodes[child];
                 const double f = s_g[i] + h;
                 n.h = h; n.f = f; n.in_open = 1;
-                oh_push(s_O, f, child);
+                oh_push(s_of, s_oi, ogf, ogi, nodes, on, f, child);
               } else {                                                    // :219-230 (in place, no re-heapify)
                 const double new_f = h + s_g[i];
                 if (new_f < s_oldf[i]) {
                   Node &n = nodes[found];
                   n.f = new_f; n.g = s_g[i]; n.h = h; n.parent = cur; n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num);
-                  if (n.hpos < AVP_SM_OPEN) s_of[n.hpos] = new_f; else s_O.gf[n.hpos - AVP_SM_OPEN] = new_f;
+                  if (n.hpos < AVP_SM_OPEN) s_of[n.hpos] = new_f; else ogf[n.hpos - AVP_SM_OPEN] = new_f;
                 }
               }
             }
@@ -843,7 +860,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
           if (stop >= nchild) break;
           // heuristic miss for successor `stop`: Dijkstra.compute_path resumes (compute_h.py:198-214)
           long long term;
-          const int d = dij_compute_path(s_D, s_cpose[stop][0], s_cpose[stop][1], &term);
+          const int d = dij_compute_path(s_D, s_heap, s_cpose[stop][0], s_cpose[stop][1], &term);
           ++n_miss;
           if (lane == 0) {
             if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
@@ -854,6 +871,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
           if (__shfl_sync(AVP_FULL_MASK, s_status, 0)) break;
           // the target cell is in the table now: lane 0 continues with successor `stop`
         }
+        if (lane == 0) s_on = on;
         if (lane == 0 && !s_status) { nodes[cur].in_closed = 1; nodes[cur].in_open = 0; s_nclosed++; s_G += nchild; }   // :235-239
       }
     }
@@ -864,7 +882,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       avp_plan_summary &R = P.sums[sc];
       int status = s_status;
       if (!status && !reached) status = (s_in_radius && s_best.ok) ? AVP_OPEN_EXHAUSTED_RS : AVP_OPEN_EXHAUSTED;
-      R.status = status; R.n_pops = s_npops; R.global_index = s_G; R.n_closed = s_nclosed; R.n_open = s_O.n;
+      R.status = status; R.n_pops = s_npops; R.global_index = s_G; R.n_closed = s_nclosed; R.n_open = s_on;
       R.last_index = s_cur; R.n_hq = s_nhq; R.h_closed = s_D.closed_len; R.nx = S.nx; R.ny = S.ny; R.n_obs = S.n_obs;
       R.n_hcalls = s_nhcalls; R.pitch[0] = S.dx; R.pitch[1] = S.dy;
       for (int i = 0; i < 4; ++i) R.boundary[i] = S.b[i];
