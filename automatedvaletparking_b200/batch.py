@@ -240,6 +240,13 @@ class DevicePlanner:
         self._ck(self._L.avp_last_search_passes(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)), "avp_last_search_passes")
         return float(a.value), float(b.value), int(n.value) % 100000, int(n.value) // 100000
 
+    def dijkstra_query(self, s: int, x: float, y: float, reset: bool = False):
+        """Dijkstra.compute_path(x, y) of scenario s -> (distance, len(closedlist), terminate_grid_id)"""
+        d, c, t = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self._L.avp_dijkstra_query(self._h, s, 1 if reset else 0, float(x), float(y), ctypes.byref(d), ctypes.byref(c), ctypes.byref(t)),
+                 "avp_dijkstra_query")
+        return d.value, c.value, t.value
+
     def phase_profile(self) -> np.ndarray:
         out = np.zeros((self.n, 8), dtype=np.int64)
         self._ck(self._L.avp_fetch_profile(self._h, out.ctypes.data_as(_native.c_lp)), "avp_fetch_profile")

@@ -41,6 +41,8 @@ struct avp_ctx {
   int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
   float pass_ms[2] = {0.f, 0.f}; int n_pending = 0; int wide_block = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+  // persistent single-scenario Dijkstra query state (drop-in for compute_h.Dijkstra)
+  int dq_scen = -1; unsigned long long *d_dq_save = nullptr, *d_dq_gheap = nullptr; DijPersist *d_dq_state = nullptr; int32_t *d_dq_out = nullptr;
   // scratch for the small API kernels
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
 };
@@ -91,7 +93,7 @@ static void free_scenarios(avp_ctx *ctx) {
   free_dev(ctx->d_col); free_dev(ctx->d_cells); free_dev(ctx->d_hval); free_dev(ctx->d_ost); free_dev(ctx->d_gx); free_dev(ctx->d_gy);
   ctx->d_scen = nullptr; ctx->d_nv = ctx->d_vert_off = nullptr; ctx->d_verts = nullptr; ctx->d_cost = nullptr; ctx->d_col = nullptr;
   ctx->d_cells = nullptr; ctx->d_hval = ctx->d_ost = nullptr; ctx->d_gx = ctx->d_gy = nullptr;
-  ctx->n = 0; ctx->rasterised = false;
+  ctx->n = 0; ctx->rasterised = false; ctx->dq_scen = -1;
 }
 static void free_results(avp_ctx *ctx) {
   free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq); free_dev(ctx->d_dbg); ctx->d_dbg = nullptr; free_dev(ctx->d_prof); ctx->d_prof = nullptr;
@@ -108,6 +110,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
   free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_worklist);
+  free_dev(ctx->d_dq_save); free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->evA) cudaEventDestroy(ctx->evA); if (ctx->evB) cudaEventDestroy(ctx->evB);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -285,11 +288,12 @@ static int ensure_ws(avp_ctx *ctx) {
   const int max_pops = ctx->cfg.max_pops > 0 ? ctx->cfg.max_pops : 20000;
   const int node_cap = nchild * (max_pops + 1) + 2;
   int slots = ctx->slots; if (slots > ctx->n) slots = ctx->n;      // no more CTAs than scenarios
+  if (slots < 1) slots = 1;
   if (ctx->ws_slots >= slots && ctx->node_cap == node_cap) return 0;
   free_ws(ctx);
   int hb = 1; while (hb < 2 * node_cap) hb <<= 1;
   ctx->node_cap = node_cap; ctx->htab_size = hb; ctx->dheap_cap = 1 << 16;
-  const int S = ctx->slots;   // allocate for the full persistent grid once
+  const int S = slots;        // as many slots as CTAs that can be resident for this batch
   CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)S * node_cap));
   CK(cudaMalloc(&ctx->d_oheap, sizeof(int32_t) * (size_t)S * node_cap));
   CK(cudaMalloc(&ctx->d_oheap_f, sizeof(double) * (size_t)S * node_cap));
@@ -349,6 +353,7 @@ static int wait_search(avp_ctx *ctx, cudaEvent_t ev) {
  * Results are identical to a single pass (a search is a deterministic function of its scenario). */
 static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   if (ctx->n <= 0) FAIL("plan: no scenarios uploaded");
+  ctx->dq_scen = -1;
   if (!ctx->rasterised) FAIL("plan: call avp_rasterise first");
   CK(cudaSetDevice(ctx->device));
   if (ensure_ws(ctx)) return -1;
@@ -534,5 +539,35 @@ extern "C" int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n) {
   if (!ctx->d_prof) FAIL("avp_fetch_profile: no results");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpy(out8n, ctx->d_prof, sizeof(long long) * (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* replaces compute_h.Dijkstra(map).compute_path(node_x, node_y) (compute_h.py:198-214) for scenario s:
+ * stateful and resumable exactly like the reference object.  reset != 0 starts a fresh Dijkstra
+ * object.  out: popped distance (-1: the reference would block forever), len(closedlist), target id.
+ * The h table it fills is readable with avp_fetch_hvalues.  avp_plan_batch reuses the same per-id
+ * arrays: a search run invalidates this state. */
+extern "C" int avp_dijkstra_query(avp_ctx *ctx, int s, int reset, double node_x, double node_y, int32_t *dist, int32_t *closed_len, int32_t *target_id) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n) FAIL("avp_dijkstra_query: scenario index out of range");
+  if (!ctx->rasterised) FAIL("avp_dijkstra_query: call avp_rasterise first");
+  CK(cudaSetDevice(ctx->device));
+  const int gcap = 1 << 20;
+  if (!ctx->d_dq_save) {
+    CK(cudaMalloc(&ctx->d_dq_save, sizeof(unsigned long long) * AVP_SM_HEAP));
+    CK(cudaMalloc(&ctx->d_dq_gheap, sizeof(unsigned long long) * gcap));
+    CK(cudaMalloc(&ctx->d_dq_state, sizeof(DijPersist)));
+    CK(cudaMalloc(&ctx->d_dq_out, sizeof(int32_t) * 4));
+    CK(cudaMemset(ctx->d_dq_state, 0, sizeof(DijPersist)));
+  }
+  if (ctx->dq_scen != s) { reset = 1; ctx->dq_scen = s; }
+  k_dij_query<<<1, 32, 0, ctx->stream>>>(ctx->d_scen, s, ctx->d_cost, ctx->d_hval, ctx->d_ost, ctx->d_gx, ctx->d_gy, ctx->d_dq_save, ctx->d_dq_gheap, gcap,
+                                         ctx->d_dq_state, reset, node_x, node_y, ctx->d_dq_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  int32_t out[4];
+  CK(cudaMemcpyAsync(out, ctx->d_dq_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (dist) *dist = out[0]; if (closed_len) *closed_len = out[1]; if (target_id) *target_id = out[2];
   return 0;
 }

@@ -419,6 +419,37 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
 #undef HP_SET
 }
 
+// Stand-alone resumable Dijkstra query (drop-in for compute_h.Dijkstra.compute_path, single-step API):
+// the queue of scenario `s` persists between launches in `save` (shared-memory part), gheap and st[].
+struct DijPersist { int hn, closed_len, status, inited; };
+
+__global__ void __launch_bounds__(32) k_dij_query(const ScenDev *scen, int s, const uint8_t *cost, int32_t *hval, int32_t *ost, double *gx, double *gy,
+                                                  unsigned long long *save, unsigned long long *gheap, int gcap, DijPersist *st,
+                                                  int reset, double x, double y, int32_t *out3) {
+  __shared__ unsigned long long s_heap[AVP_SM_HEAP];
+  __shared__ DijCtx D;
+  const ScenDev &S = scen[s];
+  const int lane = threadIdx.x;
+  if (reset || !st->inited) {
+    for (int i = lane; i < S.n_ids; i += 32) { hval[S.id_off + i] = -1; ost[S.id_off + i] = -1; }
+    if (lane == 0) { st->hn = 0; st->closed_len = 0; st->status = 0; st->inited = 1; }
+    __syncwarp();
+  }
+  const int hn0 = st->hn;
+  for (int i = lane; i < hn0 && i < AVP_SM_HEAP; i += 32) s_heap[i] = save[i];
+  if (lane == 0) {
+    D.S = &S; D.cost = cost + S.cost_off; D.hval = hval + S.id_off; D.ost = ost + S.id_off; D.gx = gx + S.id_off; D.gy = gy + S.id_off;
+    D.sheap = s_heap; D.gheap = gheap; D.gcap = gcap; D.hn = hn0; D.closed_len = st->closed_len; D.status = 0;
+  }
+  __syncwarp();
+  long long term;
+  const int d = dij_compute_path(D, s_heap, x, y, &term);
+  __syncwarp();
+  const int hn1 = D.hn;
+  for (int i = lane; i < hn1 && i < AVP_SM_HEAP; i += 32) save[i] = s_heap[i];
+  if (lane == 0) { st->hn = hn1; st->closed_len = D.closed_len; st->status = D.status; out3[0] = d; out3[1] = D.closed_len; out3[2] = (int)term; out3[3] = D.status; }
+}
+
 // ------------------------------------------------------------------------------------------
 // hybrid A* containers (per slot)
 

@@ -1,0 +1,142 @@
+"""Drop-in for path_plan/path_planner.py: PathPlanner (path_planner.py:25-192).
+
+a_star_plan() runs the WHOLE search on the GPU (avp_plan_batch: raster, lazy Dijkstra heuristic,
+successor expansion, rs shots) and returns the reference's tuple (final_path, astar_path, PATH);
+path_planning() adds split_path (gear-change splitting with collision-checked extension points,
+path_planner.py:112-192; its checks run on the GPU).  A search the reference cannot finish raises
+the same exception class the reference raises (AttributeError for an exhausted open list)."""
+import copy
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from .hybrid_a_star import hybrid_a_star
+from ..map.costmap import Vehicle, Map
+from ..collision_check import collision_check
+from .rs_curve import PATH
+from . import rs_curve
+
+
+class PlanningCapacityError(RuntimeError):
+    """the search exceeded max_pops (the reference would keep running)"""
+
+
+class PathPlanner:
+    def __init__(self, config: dict = None, map: Map = None, vehicle: Vehicle = None, max_pops: int = 20000, verbose: bool = False) -> None:
+        self.config = config
+        self.map = map
+        self.vehicle = vehicle
+        self.verbose = verbose
+        self.max_pops = max_pops
+        if config['collision_check'] == 'circle':
+            self.collision_checker = collision_check.two_circle_checker(map=map, vehicle=vehicle, config=config)
+        else:
+            self.collision_checker = collision_check.distance_checker(map=map, vehicle=vehicle, config=config)
+        self._planner = None
+        self.last_summary = None
+        self.pop_indices = None
+
+    @property
+    def planner(self) -> hybrid_a_star:
+        """the reference builds hybrid_a_star eagerly (path_planner.py:42-43); here the step-wise object is
+        only materialised when somebody asks for it (a_star_plan does not need it)"""
+        if self._planner is None:
+            self._planner = hybrid_a_star(config=self.config, park_map=self.map, vehicle=self.vehicle)
+        return self._planner
+
+    def path_planning(self) -> Tuple[List[List], Dict, List[List[List]]]:
+        final_path, astar_path, rs_path = self.a_star_plan()
+        split_path_list, change_gear = self.split_path(final_path)
+        path_info = {'astar_path': astar_path, 'rs_path': rs_path, 'change_gear': change_gear}
+        out_final_path = sum(split_path_list, [])
+        return out_final_path, path_info, split_path_list
+
+    def a_star_plan(self) -> Tuple[List[List], List[List], PATH]:
+        from ..batch import DevicePlanner
+        dev = DevicePlanner(self.config, self.vehicle, max_pops=self.max_pops)
+        try:
+            dev.load([self.map.scenario])
+            res = dev.plan(cap_path=4096, cap_pops=self.max_pops)
+        finally:
+            pass
+        s = res.summaries[0]
+        self.last_summary = s
+        self.pop_indices = res.pop_indices(0).copy()
+        if self.verbose:                                   # the reference prints every pop (path_planner.py:72-76)
+            for idx in self.pop_indices:
+                print('---------------')
+                print('current node index:', int(idx))
+                print('---------------')
+        status = int(s['status'])
+        dev.close()
+        if status == 1:
+            raise AttributeError("'NoneType' object has no attribute 'x'")        # path_planner.py:104 on an exhausted open list
+        if status == 3:
+            raise RuntimeError("heuristic target unreachable: the reference blocks forever (compute_h.py:77)")
+        if status == 4:
+            raise AssertionError("path.L >= 0.01")                               # rs_curve.py:153
+        if status == 5:
+            raise PlanningCapacityError(f"no path within max_pops={self.max_pops}")
+        if status == 6:
+            raise TypeError("only size-1 arrays can be converted to Python scalars")
+        path = res.path(0)
+        n_astar, n_rs = int(s['n_astar']), int(s['n_rs'])
+        a_star_path = [[np.float64(p[0]), np.float64(p[1]), np.float64(p[2])] for p in path[:n_astar]]
+        final_path = copy.deepcopy(a_star_path) + [[float(p[0]), float(p[1]), float(p[2])] for p in path[n_astar:]]
+        # the PATH object of the successful shot: word, lengths and course (course from the device path rows)
+        last = path[n_astar - 1]
+        nseg = int(s['rs_nseg'])
+        rs_x = [float(last[0])] + [float(p[0]) for p in path[n_astar:]]
+        rs_y = [float(last[1])] + [float(p[1]) for p in path[n_astar:]]
+        rs_yaw = [float(last[2])] + [float(p[2]) for p in path[n_astar:]]
+        full = rs_curve.calc_optimal_path(a_star_path[-1][0], a_star_path[-1][1], a_star_path[-1][2] if n_astar > 1 else float(last[2]),
+                                          self.map.case.xf, self.map.case.yf, rs_curve.pi_2_pi(self.map.case.thetaf), 1 / self.vehicle.min_radius_turn)
+        rs_path = PATH([float(v) for v in s['rs_lengths'][:nseg]], list(s['rs_ctypes'].decode()), float(s['rs_L']), rs_x, rs_y, rs_yaw,
+                       full.directions if len(full.directions) == n_rs else [0] * n_rs)
+        return final_path, a_star_path, rs_path
+
+    def split_path(self, final_path: List[List]) -> Tuple[List[List[List]], int]:
+        """path_planner.py:112-192"""
+        from scipy import spatial
+        split_path = []
+        change_gear = 0
+        start = 0
+        extend_num = self.config['extended_num']
+        have_extended_points = 0
+        ddt = self.config['trajectory_dt']
+        for i in range(len(final_path) - 2):
+            vector_1 = (final_path[i + 1][0] - final_path[i][0], final_path[i + 1][1] - final_path[i][1])
+            vector_2 = (final_path[i + 2][0] - final_path[i + 1][0], final_path[i + 2][1] - final_path[i + 1][1])
+            compute_cosin = 1 - spatial.distance.cosine(vector_1, vector_2)
+            if compute_cosin < 0:
+                change_gear += 1
+                end = i + 2
+                input_path = final_path[start:end]
+                if change_gear > 1 and have_extended_points > 0:
+                    pre_path = split_path[-1]
+                    for j in range(have_extended_points):
+                        p = pre_path[-(have_extended_points - j)]
+                        input_path.insert(0, [p[0], p[1], p[2]])
+                    have_extended_points = 0
+                for j in range(extend_num):
+                    th_i = final_path[i][2]
+                    forward_1 = (final_path[i + 1][0] > final_path[i][0]) and (-np.pi / 2 < th_i < np.pi / 2)
+                    forward_2 = (final_path[i + 1][0] < final_path[i][0]) and ((np.pi / 2 < th_i < np.pi) or (-np.pi < th_i < -np.pi / 2))
+                    speed = self.vehicle.max_v if (forward_1 or forward_2) else -self.vehicle.max_v
+                    td_j = speed * ddt * (j + 1)
+                    theta_j = final_path[i + 1][2]
+                    x_j = final_path[i + 1][0] + td_j * np.cos(theta_j)
+                    y_j = final_path[i + 1][1] + td_j * np.sin(theta_j)
+                    if not self.collision_checker.check(node_x=x_j, node_y=y_j, theta=theta_j):
+                        input_path.append([x_j, y_j, theta_j])
+                        have_extended_points += 1
+                split_path.append(input_path)
+                start = i + 1
+        input_path = final_path[start:]
+        pre_path = split_path[-1]
+        if have_extended_points > 0:
+            for j in range(have_extended_points):
+                p = pre_path[-(have_extended_points - j)]
+                input_path.insert(0, [p[0], p[1], p[2]])
+        split_path.append(input_path)
+        return split_path, int(change_gear)

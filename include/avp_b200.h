@@ -173,6 +173,13 @@ int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block)
  * hval[id] = distance of the first closedlist entry with grid_id == id, -1 if none. */
 int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *n_ids);
 
+/* replaces compute_h.Dijkstra(map).compute_path(node_x, node_y) (compute_h.py:198-214) for scenario s:
+ * stateful and resumable like the reference object; reset != 0 starts a fresh Dijkstra object.
+ * dist = popped distance of the target cell (-1: the reference would block forever in queue.get()),
+ * closed_len = len(closedlist), target_id = terminate_grid_id.  The h table is read with
+ * avp_fetch_hvalues.  A plan run reuses the per-id arrays and invalidates this state. */
+int avp_dijkstra_query(avp_ctx *ctx, int s, int reset, double node_x, double node_y, int32_t *dist, int32_t *closed_len, int32_t *target_id);
+
 /* CUDA-event stopwatch on the context's stream around any sequence of entry points, and the
  * CUDA-event duration of the most recent search-kernel launch (bench.py timing legs) */
 int avp_timer_start(avp_ctx *ctx);

@@ -27,8 +27,21 @@ def test_oracle_reproduces_reference_trace(path, cfg):
     ix, iy = np.where(m.cost_map() == 255)
     assert np.array_equal(np.stack([ix, iy], 1).astype(np.uint16), g["obs_cells"])
     # search (path_planner.py:58-110)
-    r = O.plan(m, cfg)
     status = str(g["status"])
+    if status == "truncated":
+        # Cases 7, 8, 19 never finish in the reference: its first pops are pinned.
+        # The reference was stopped right after taking pop n+1 from the open list, before expanding it.
+        from automatedvaletparking_b200.hostcfg import make_avp_config
+        n = len(g["pops"])
+        r = O.plan(m, make_avp_config(max_pops=n))
+        assert r["status"] == 5 and r["n_pops"] == n
+        assert np.array_equal(r["pops"], g["pops"]) and np.array_equal(r["pop_state"], g["pop_state"])
+        assert np.array_equal(r["pop_fgh"], g["pop_fgh"])
+        assert np.array_equal(r["hq"], g["hq"][:len(r["hq"])]) and r["n_hq"] == len(g["hq"])
+        assert r["global_index"] == int(g["global_index"]) and r["n_closed"] == int(g["n_closed"])
+        assert r["n_open"] == int(g["n_open"]) + 1          # the reference had already popped node n+1
+        return
+    r = O.plan(m, cfg)
     assert r["status"] == (0 if status == "ok" else 1)
     assert np.array_equal(r["pops"], g["pops"])                       # expanded-node indices
     assert np.array_equal(r["pop_state"], g["pop_state"])             # bit-exact poses
@@ -49,7 +62,6 @@ def test_oracle_reproduces_reference_trace(path, cfg):
         assert np.array_equal(r["rs_dir"], g["rs_dir"])
 
 
-def test_all_benchmark_cases_have_or_await_goldens():
+def test_all_benchmark_cases_are_pinned():
     have = {int(os.path.basename(p)[4:-4]) for p in CASES}
-    # Cases 7, 8, 19 need hours in the reference; everything else must be pinned
-    assert have >= set(range(1, 21)) - {7, 8, 19}
+    assert have == set(range(1, 21))
