@@ -75,12 +75,16 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<AVP_BLOCK_NARROW>, AVP_BLOCK_NARROW, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  cudaFuncSetAttribute(k_search<AVP_BLOCK_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(AVP_BLOCK_NARROW));
+  cudaFuncSetAttribute(k_search<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(128));
+  cudaFuncSetAttribute(k_search<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
+  cudaFuncSetAttribute(k_search<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<AVP_BLOCK_NARROW>, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW)) != cudaSuccess || per_sm < 1) per_sm = 1;
   ctx->slots = ctx->n_sm * per_sm;               // persistent grids: multiples of the SM count
   int o = 0;
-  ctx->slots_w[0] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<512>, 512, 0) == cudaSuccess && o > 0) ? o : 1);
-  ctx->slots_w[1] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<256>, 256, 0) == cudaSuccess && o > 0) ? o : 1);
-  ctx->slots_w[2] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<128>, 128, 0) == cudaSuccess && o > 0) ? o : 1);
+  ctx->slots_w[0] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<512>, 512, 12 * avp_sm_open(512)) == cudaSuccess && o > 0) ? o : 1);
+  ctx->slots_w[1] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<256>, 256, 12 * avp_sm_open(256)) == cudaSuccess && o > 0) ? o : 1);
+  ctx->slots_w[2] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<128>, 128, 12 * avp_sm_open(128)) == cudaSuccess && o > 0) ? o : 1);
   ctx->slots_wide = ctx->slots_w[0];
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
@@ -371,7 +375,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_search<AVP_BLOCK_NARROW><<<grid, AVP_BLOCK_NARROW, 0, ctx->stream>>>(P); ctx->launches++;
+  k_search<AVP_BLOCK_NARROW><<<grid, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW), ctx->stream>>>(P); ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());
   if (wait_search(ctx, ctx->ev1)) return -1;
@@ -400,10 +404,10 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       int grid2 = cap; if (grid2 > npend) grid2 = npend; if (grid2 > ctx->ws_slots) grid2 = ctx->ws_slots;
       ctx->wide_block = which == 0 ? 512 : which == 1 ? 256 : which == 2 ? 128 : AVP_BLOCK_NARROW;
       CK(cudaEventRecord(ctx->ev0, ctx->stream));
-      if (which == 0) k_search<512><<<grid2, 512, 0, ctx->stream>>>(P);
-      else if (which == 1) k_search<256><<<grid2, 256, 0, ctx->stream>>>(P);
-      else if (which == 2) k_search<128><<<grid2, 128, 0, ctx->stream>>>(P);
-      else k_search<AVP_BLOCK_NARROW><<<grid2, AVP_BLOCK_NARROW, 0, ctx->stream>>>(P);
+      if (which == 0) k_search<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
+      else if (which == 1) k_search<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
+      else if (which == 2) k_search<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
+      else k_search<AVP_BLOCK_NARROW><<<grid2, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW), ctx->stream>>>(P);
       ctx->launches++;
       CK(cudaEventRecord(ctx->ev1, ctx->stream));
       CK(cudaGetLastError());

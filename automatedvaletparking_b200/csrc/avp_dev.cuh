@@ -221,10 +221,11 @@ __device__ __forceinline__ bool cell_hits(const VehGeom &g, double ox, double oy
 // the np.where order, which is sorted by column).
 __device__ __forceinline__ void col_range(const ScenDev &S, double x_min, double x_max, int &lo, int &hi) {
   const int nx = S.nx;
-  int a = (int)floor((x_min - S.b[0]) / S.stepx) - 1; if (a < 0) a = 0; if (a > nx - 1) a = nx - 1;
+  const double inv = 1.0 / S.stepx;                 // initial guesses only: the loops below settle the exact bounds
+  int a = (int)floor((x_min - S.b[0]) * inv) - 1; if (a < 0) a = 0; if (a > nx - 1) a = nx - 1;
   while (a > 0 && lin_at(S.b[0], S.b[1], S.stepx, nx, a - 1) >= x_min) --a;
   while (a < nx && !(lin_at(S.b[0], S.b[1], S.stepx, nx, a) >= x_min)) ++a;
-  int b = (int)floor((x_max - S.b[0]) / S.stepx) + 1; if (b > nx - 1) b = nx - 1; if (b < 0) b = 0;
+  int b = (int)floor((x_max - S.b[0]) * inv) + 1; if (b > nx - 1) b = nx - 1; if (b < 0) b = 0;
   while (b < nx - 1 && lin_at(S.b[0], S.b[1], S.stepx, nx, b + 1) <= x_max) ++b;
   while (b >= 0 && !(lin_at(S.b[0], S.b[1], S.stepx, nx, b) <= x_max)) --b;
   lo = a; hi = b;

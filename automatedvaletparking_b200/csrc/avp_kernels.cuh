@@ -485,9 +485,10 @@ __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node 
 // Entries carry a copy of f (kept in sync on the reference's in-place updates through Node.hpos);
 // the first AVP_SM_OPEN entries live in shared memory.  The functions are force-inlined and take
 // the __shared__ arrays themselves so that the compiler keeps the shared address space.
-#define OH_F(i) ((i) < AVP_SM_OPEN ? sf[(i)] : gf[(i) - AVP_SM_OPEN])
-#define OH_I(i) ((i) < AVP_SM_OPEN ? si[(i)] : gi[(i) - AVP_SM_OPEN])
-#define OH_SET(i, f_, idx_) do { if ((i) < AVP_SM_OPEN) { sf[(i)] = (f_); si[(i)] = (idx_); } else { gf[(i) - AVP_SM_OPEN] = (f_); gi[(i) - AVP_SM_OPEN] = (idx_); } nodes[(idx_)].hpos = (i); } while (0)
+#define OH_F(i) ((i) < SMO ? sf[(i)] : gf[(i) - SMO])
+#define OH_I(i) ((i) < SMO ? si[(i)] : gi[(i) - SMO])
+#define OH_SET(i, f_, idx_) do { if ((i) < SMO) { sf[(i)] = (f_); si[(i)] = (idx_); } else { gf[(i) - SMO] = (f_); gi[(i) - SMO] = (idx_); } nodes[(idx_)].hpos = (i); } while (0)
+template <int SMO>
 __device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int pos, double fi, int item) {   // heapq._siftdown(heap, 0, pos)
   while (pos > 0) {
     const int parent = (pos - 1) >> 1; const double pf = OH_F(parent);
@@ -496,11 +497,13 @@ __device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, double *gf,
   }
   OH_SET(pos, fi, item);
 }
+template <int SMO>
 __device__ __forceinline__ void oh_push(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int &n, double f, int idx) {
   const int pos = n++;
-  oh_siftdown(sf, si, gf, gi, nodes, pos, f, idx);
+  oh_siftdown<SMO>(sf, si, gf, gi, nodes, pos, f, idx);
 }
 // heapq.heappop after the root has been read: move the last entry to the root and _siftup
+template <int SMO>
 __device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int &n) {
   const int last = n - 1;
   const double fi = OH_F(last); const int item = OH_I(last);
@@ -514,7 +517,7 @@ __device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, double *gf, 
     const int ci = OH_I(child);
     OH_SET(pos, cf, ci); pos = child; child = 2 * pos + 1;
   }
-  oh_siftdown(sf, si, gf, gi, nodes, pos, fi, item);
+  oh_siftdown<SMO>(sf, si, gf, gi, nodes, pos, fi, item);
 }
 
 // hybrid_a_star.py:243-259
@@ -540,12 +543,18 @@ __device__ __forceinline__ void child_pose(const avp_config &cfg, const Node &cn
 
 enum { CTL_RUN = 0, CTL_EXIT = 1 };
 
+// shared-memory entries of the open heap per CTA width (dynamic shared memory: 12 bytes per entry)
+__host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? 2048 : 1024; }   // more shared memory here costs L1 hit rate (libm tables, nodes)
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 4)) k_search(KParams P) {
   constexpr int NWARPS = BLOCK / 32;
+  constexpr int SMO = avp_sm_open(BLOCK);
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double *s_of = reinterpret_cast<double *>(s_dyn);
+  int32_t *s_oi = reinterpret_cast<int32_t *>(s_dyn + sizeof(double) * SMO);
+  constexpr int CW0 = (NWARPS >= 8) ? 4 : (NWARPS / 2);        // warps [CW0, NWARPS): collision checks; [0, CW0): word selection
   __shared__ unsigned long long s_heap[AVP_SM_HEAP];
-  __shared__ double s_of[AVP_SM_OPEN];
-  __shared__ int32_t s_oi[AVP_SM_OPEN];
   __shared__ RsCand s_cand[AVP_NCHILD_MAX + 1][RS_NINST];
   __shared__ unsigned long long s_valid[AVP_NCHILD_MAX + 1];
   __shared__ double s_cpose[AVP_NCHILD_MAX][3];
@@ -620,7 +629,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
         r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0; r.pad1 = 0;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
-        { int n_ = s_on; oh_push(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
+        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
       }
     }
 
@@ -658,7 +667,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
 
       // phase 0: successor poses and the normalised rs queries (threads 32.. so that thread 0 can
       //          finish heapq.heappop meanwhile: move the last entry to the root, sift)
-      if (tid == 0) { int n_ = s_on; oh_pop_fix(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; }
+      if (tid == 0) { int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; }
       {
         const int t0 = (BLOCK >= 64) ? 32 : 0;       // keep thread 0's warp free for the heap
         const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
@@ -682,8 +691,26 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       }
       __syncthreads();
       AVP_TICK(2);                             // heappop + poses/queries
-      // phase 1a: the warps take the successors: closed/open lookup, sub-step collision checks (hybrid_a_star.py:154-204)
-      for (int i = warp; i < nchild; i += NWARPS) {
+      // phase 1: rs word instances: row nchild = the goal shot of the popped node, rows 0..nchild-1 = successors
+      // (speculative for successors that turn out skipped / colliding)
+      // item = inst * (nchild + 1) + row: the lanes of a warp evaluate the SAME word formula for different
+      // poses (instances of one family are adjacent), instead of 32 different formulas
+      for (int item = tid; item < (nchild + 1) * RS_NINST; item += BLOCK) {
+        const int inst = item / (nchild + 1), row = item - inst * (nchild + 1);
+        if (row == nchild && !s_in_radius) continue;
+        double t, u, v;
+        if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
+          RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
+          c.L = rs_cand_L(inst, c, 1, (row == nchild) ? phi_np : 1);
+          s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
+        }
+      }
+      __syncthreads();
+      AVP_TICK(3);                             // rs instances
+      // phase 2a, two groups of warps concurrently:
+      //   warps CW0..  : the successors' closed/open lookup and sub-step collision checks (hybrid_a_star.py:154-204)
+      //   warps 0..CW0-1: set_path de-duplication + minimum per (row, ctype group)
+      for (int i = warp - CW0; i >= 0 && i < nchild; i += NWARPS - CW0) {
         const double x_ = s_cpose[i][0], y_ = s_cpose[i][1], th = s_cpose[i][2];
         int found = -1, skip = 0;
         if (lane == 0) {
@@ -711,27 +738,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
         }
         if (lane == 0) { s_coll[i] = coll; s_need[i] = (!skip) && ((found < 0 && !coll) || (found >= 0)); }
       }
-      // phase 1b: rs word instances: row nchild = the goal shot of the popped node, rows 0..nchild-1 = successors
-      // (speculative for successors that turn out skipped / colliding: it needs no barrier after 1a)
-      // item = inst * (nchild + 1) + row: the lanes of a warp evaluate the SAME word formula for different
-      // poses (instances of one family are adjacent), instead of 32 different formulas
-      for (int item = tid; item < (nchild + 1) * RS_NINST; item += BLOCK) {
-        const int inst = item / (nchild + 1), row = item - inst * (nchild + 1);
-        if (row == nchild && !s_in_radius) continue;
-        double t, u, v;
-        if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
-          RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
-          c.L = rs_cand_L(inst, c, 1, (row == nchild) ? phi_np : 1);
-          s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
-        }
-      }
-      __syncthreads();
-      AVP_TICK(3);                             // lookups, collision checks, rs instances
-
       // phase 2a: set_path de-duplication + minimum per (row, ctype group) in parallel
-      for (int item = tid; item < (nchild + 1) * RS_NGROUP; item += BLOCK) {
+      for (int item = tid; tid < CW0 * 32 && item < (nchild + 1) * RS_NGROUP; item += CW0 * 32) {
         const int g = item / (nchild + 1), row = item - g * (nchild + 1);       // group-major: same code path per warp
-        if (row == nchild ? !s_in_radius : !s_need[row]) continue;
+        if (row == nchild && !s_in_radius) continue;          // successors: unconditionally (their collision flags are being computed concurrently)
         rs_select_group(s_cand[row], s_valid[row], g, 1, (row == nchild) ? phi_np : 1, maxc, s_grp[row][g]);
       }
       __syncthreads();
@@ -744,41 +754,54 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
           s_rsL[tid] = b.ok ? b.L / maxc : 0.0;
         }
       }
-      const int shot_tid = (BLOCK > 32) ? 32 : nchild;
-      if (tid == shot_tid && s_in_radius) {
-        RsBest b; rs_combine_groups(s_grp[nchild], s_cand[nchild], 1, phi_np, b);
-        if (!b.ok || b.degenerate) s_shot_bad = 1;
-        else {
-          // generate_local_course (rs_curve.py:537-594), sequential part: which (segment, arc length)
-          // writes each point index last, and the segment origins
-          const double step = 0.5 * maxc;
-          const int point_num = (int)(b.L / step) + b.n + 3;
-          if (point_num > AVP_COURSE_CAP) s_shot_bad = 2;
-          else {
-            const char *mode = rs_ct_names[b.ct];
-            s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
-            int ind = 1; double d, pd, ll = 0.0;
-            CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
-            for (int i = 0; i < b.n; ++i) {
-              const double l = b.len[i];
-              d = (l > 0.0) ? step : -step;
-              ind -= 1;
-              if (i >= 1 && (b.len[i - 1] * b.len[i]) > 0) pd = -d - ll; else pd = d - ll;
-              while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
-              if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
-              ll = l - pd - d;
-              ind += 1; CYAW[ind] = l; CDIR[ind] = i;
-              int dir;
-              rs_interpolate(l, mode[i], maxc, s_org[i][0], s_org[i][1], s_org[i][2], s_org[i + 1][0], s_org[i + 1][1], s_org[i + 1][2], dir);
-              if (mode[i] == 'S') s_org[i + 1][2] = s_org[i][2];
-            }
-            s_nplan = ind + 1;
+      {
+        // the shot's word, then its course plan (generate_local_course, rs_curve.py:537-594): lane 0 of the
+        // shot warp combines the groups; lanes 0..n-1 evaluate the segments' end-point increments in
+        // parallel (they only depend on the arc lengths); lane 0 accumulates the segment origins and
+        // records which (segment, arc length) writes each point index last.
+        constexpr int SHOT_WARP = (NWARPS > 1) ? 1 : 0;
+        if (warp == SHOT_WARP && s_in_radius) {
+          if (lane == 0) {
+            RsBest b; rs_combine_groups(s_grp[nchild], s_cand[nchild], 1, phi_np, b);
+            if (!b.ok || b.degenerate) s_shot_bad = 1;
+            else if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
             s_best = b;
+          }
+          __syncwarp();
+          if (!s_shot_bad) {
+            const int nseg = s_best.n;
+            const char *mode = rs_ct_names[s_best.ct];
+            if (lane < nseg) {
+              double oyaw = 0.0;                                        // heading at the start of segment `lane`
+              for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
+              double ix, iy, yaw_next = oyaw; int dir;
+              rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
+              s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;    // increments for now
+            }
+            __syncwarp();
+            if (lane == 0) {
+              const double step = 0.5 * maxc;
+              s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
+              for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
+              int ind = 1; double d, pd, ll = 0.0;
+              CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
+              for (int i = 0; i < nseg; ++i) {
+                const double l = s_best.len[i];
+                d = (l > 0.0) ? step : -step;
+                ind -= 1;
+                if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
+                while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
+                if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
+                ll = l - pd - d;
+                ind += 1; CYAW[ind] = l; CDIR[ind] = i;
+              }
+              s_nplan = ind + 1;
+            }
           }
         }
       }
       __syncthreads();
-      AVP_TICK(4);                             // selection + course plan
+      AVP_TICK(4);                             // lookups + collision checks || selection; combine + course plan
       if (s_shot_bad) { if (tid == 0) s_status = (s_shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; continue; }
 
       if (s_in_radius) {
@@ -875,13 +898,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
                 Node &n = nodes[child];
                 const double f = s_g[i] + h;
                 n.h = h; n.f = f; n.in_open = 1;
-                oh_push(s_of, s_oi, ogf, ogi, nodes, on, f, child);
+                oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, on, f, child);
               } else {                                                    // :219-230 (in place, no re-heapify)
                 const double new_f = h + s_g[i];
                 if (new_f < s_oldf[i]) {
                   Node &n = nodes[found];
                   n.f = new_f; n.g = s_g[i]; n.h = h; n.parent = cur; n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num);
-                  if (n.hpos < AVP_SM_OPEN) s_of[n.hpos] = new_f; else ogf[n.hpos - AVP_SM_OPEN] = new_f;
+                  if (n.hpos < SMO) s_of[n.hpos] = new_f; else ogf[n.hpos - SMO] = new_f;
                 }
               }
             }
