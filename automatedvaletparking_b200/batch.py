@@ -248,7 +248,7 @@ class DevicePlanner:
         return d.value, c.value, t.value
 
     def phase_profile(self) -> np.ndarray:
-        out = np.zeros((self.n, 8), dtype=np.int64)
+        out = np.zeros((self.n, 16), dtype=np.int64)
         self._ck(self._L.avp_fetch_profile(self._h, out.ctypes.data_as(_native.c_lp)), "avp_fetch_profile")
         return out
 

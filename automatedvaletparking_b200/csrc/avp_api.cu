@@ -318,8 +318,8 @@ static int ensure_results(avp_ctx *ctx, int cap_path, int cap_pops) {
   CK(cudaMalloc(&ctx->d_pops, sizeof(int32_t) * n * (size_t)(cap_pops > 0 ? cap_pops : 1)));
   CK(cudaMalloc(&ctx->d_hq, sizeof(int32_t) * n * AVP_HQ_CAP * 3));
   CK(cudaMalloc(&ctx->d_dbg, sizeof(int) * n * 8));
-  CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * n * 8));
-  CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * n * 8));
+  CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * n * 16));
+  CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * n * 16));
   CK(cudaMemset(ctx->d_dbg, 0, sizeof(int) * n * 8));
   ctx->res_n = ctx->n; ctx->cap_path = cap_path; ctx->cap_pops = cap_pops;
   return 0;
@@ -537,12 +537,14 @@ extern "C" int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_p
 
 /* per-scenario SM-cycle accumulators of the search kernel's phases (thread 0 of the CTA):
  * [0] init + eager Dijkstra, [1] loop top, [2] heappop + poses/queries, [3] lookups + collision checks +
- * rs instances, [4] selection + course plan, [5] course + shot check, [6] commit, [7] commit preparation */
+ * rs instances, [4] selection + course plan, [5] course + shot check, [6] commit, [7] commit preparation,
+ * [8] cycles in open-heap pushes, [9] pushes, [10] cycles in Dijkstra resumes during commits, [11] resumes,
+ * [12] sum of final heap positions of pushed nodes, [13] cycles in heappop, [14] sum of heap sizes at pops */
 extern "C" int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n) {
   if (!ctx) return -3;
   if (!ctx->d_prof) FAIL("avp_fetch_profile: no results");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(out8n, ctx->d_prof, sizeof(long long) * (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out8n, ctx->d_prof, sizeof(long long) * (size_t)ctx->n * 16, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -33,7 +33,7 @@ struct __align__(16) Node {
   int32_t parent;
   uint8_t forward, steer_idx, in_open, in_closed;
   int32_t hpos;            // position of this node's entry in the open heap (valid while in_open)
-  int32_t pad1;
+  int32_t in_radius;       // distance to the goal < flag_radius (hybrid_a_star.py:308-310), evaluated when the node is created
 };
 static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
 
@@ -65,7 +65,7 @@ struct KParams {
   const int32_t *work_list;       // NULL: scenarios 0..n_work-1; else the ids to process (pass 2)
   int n_work;
   int pop_budget;                 // pass 1: a scenario still searching after this many pops ends AVP_PENDING
-  long long *prof;                // n * 8 SM-cycle accumulators per scenario (thread 0): phases of the main loop, may be NULL
+  long long *prof;                // n * 16 SM-cycle accumulators / counters per scenario (thread 0): phases of the main loop, may be NULL
   int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
   long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY
 };
@@ -285,6 +285,14 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
   return ((unsigned long long)hi << 32) | lo;
 }
 
+// floor(a / d) for d > 0, exactly as IEEE division followed by floor: the quotient estimated with the
+// reciprocal decides unless it lies within 1e-9 of an integer, where the true division is performed.
+__device__ __forceinline__ long long floor_div_exact(double a, double d, double inv_d) {
+  const double q = a * inv_d, f = floor(q), r = q - f;
+  if (r > 1e-9 && r < 1.0 - 1e-9 && fabs(q) < 1e5) return (long long)f;   // |q - a/d| <= 4 ulp(q) < 1e-10 here
+  return (long long)floor(a / d);
+}
+
 // Dijkstra.compute_path (compute_h.py:198-214); warp-collective.  Returns the popped distance of the
 // target cell, or -1 if the queue ran dry (reference: blocks forever) / capacity.
 // `sheap` must be the kernel's __shared__ heap array (the function is inlined so that the
@@ -298,6 +306,7 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
   const double b0 = S.b[0], b1 = S.b[1], b2 = S.b[2], b3 = S.b[3], dx = S.dx, dy = S.dy;
   const int nx = S.nx, ny = S.ny, mx = S.mx, my = S.my, stride = S.stride, n_ids = S.n_ids;
   int hn = D.hn, closed_len = D.closed_len, status = 0;
+  const double inv_dx = 1.0 / dx, inv_dy = 1.0 / dy;
 
 #define HP_GET(i) ((i) < AVP_SM_HEAP ? sheap[(i)] : gheap[(i) - AVP_SM_HEAP])
 #define HP_SET(i, v) do { if ((i) < AVP_SM_HEAP) sheap[(i)] = (v); else gheap[(i) - AVP_SM_HEAP] = (v); } while (0)
@@ -320,9 +329,9 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
       const int ddy = (lane < 3) ? 1 : ((lane < 5) ? 0 : -1);
       const double ngx = ddx < 0 ? cur_x - dx : (ddx > 0 ? cur_x + dx : cur_x);
       const double ngy = ddy < 0 ? cur_y - dy : (ddy > 0 ? cur_y + dy : cur_y);
-      const long long qx = (long long)floor((ngx - b0) / dx);                 // shared by is_obstacle and convert_position_to_index
+      const long long qx = floor_div_exact(ngx - b0, dx, inv_dx);             // shared by is_obstacle and convert_position_to_index
       // is_obstacle (compute_h.py:237-255)
-      long long xi = qx - 1, yi = (long long)floor((ngy - b2) / dy) - 1;
+      long long xi = qx - 1, yi = floor_div_exact(ngy - b2, dy, inv_dy) - 1;
       if (xi >= mx) xi = mx - 1; if (yi >= my) yi = my - 1;
       if (xi < 0) xi += nx; if (yi < 0) yi += ny;             // python negative indexing
       bool obstacle = false;
@@ -332,7 +341,7 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
         if (ddx < 0 && !(ngx >= b0)) ok = false; if (ddx > 0 && !(ngx <= b1)) ok = false;
         if (ddy > 0 && !(ngy <= b3)) ok = false; if (ddy < 0 && !(ngy >= b2)) ok = false;
         if (ok) {
-          const long long id = qx + (long long)floor((b3 - ngy) / dy) * (long long)stride;   // costmap.py:319-329
+          const long long id = qx + floor_div_exact(b3 - ngy, dy, inv_dy) * (long long)stride;   // costmap.py:319-329
           if (id >= 0 && id < n_ids) {
             nid = (int)id;
             const int st = ost[nid];
@@ -379,9 +388,11 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
     if (status) break;
     if (hn == 0) { status = AVP_H_UNREACHABLE; break; }
     // update_closedlist (:74-82): heappop
-    unsigned long long top = 0ull;
+    unsigned long long top = (lane == 0) ? sheap[0] : 0ull;
+    top = shfl_u64(top, 0);
+    const int cur_id = (int)(unsigned)top;
+    const double nxt_x = gxa[cur_id], nxt_y = gya[cur_id];     // issued before the sift so that the latency overlaps it
     if (lane == 0) {
-      top = sheap[0];
       const unsigned long long item = HP_GET(hn - 1);
       const int n = hn - 1;
       if (n > 0) {                            // heapq._siftup
@@ -405,12 +416,10 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
       if (hval[id] < 0) hval[id] = (int)(top >> 32);
     }
     hn -= 1; closed_len++;
-    top = shfl_u64(top, 0);
-    const int cur_id = (int)(unsigned)top;
     cur_dist = (int)(top >> 32);
     __syncwarp();
     if ((long long)cur_id == term) { result = cur_dist; break; }
-    cur_x = gxa[cur_id]; cur_y = gya[cur_id];
+    cur_x = nxt_x; cur_y = nxt_y;
   }
   if (lane == 0) { D.hn = hn; D.closed_len = closed_len; if (status) D.status = status; }
   __syncwarp();
@@ -563,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
   __shared__ RsQuery s_Q[AVP_NCHILD_MAX + 1];
   __shared__ double s_sub[AVP_NCHILD_MAX][4][4];          // sub-step poses of the successors: x, y, cos, sin (hybrid_a_star.py:185-194)
   __shared__ RsGroupBest s_grp[AVP_NCHILD_MAX + 1][RS_NGROUP];
-  __shared__ double s_g[AVP_NCHILD_MAX], s_oldf[AVP_NCHILD_MAX];
+  __shared__ double s_g[AVP_NCHILD_MAX], s_oldf[AVP_NCHILD_MAX], s_h1[AVP_NCHILD_MAX];
   __shared__ int s_found[AVP_NCHILD_MAX], s_coll[AVP_NCHILD_MAX], s_need[AVP_NCHILD_MAX], s_rsok[AVP_NCHILD_MAX], s_skip[AVP_NCHILD_MAX], s_hv[AVP_NCHILD_MAX];
   __shared__ int s_scen, s_ctl, s_cur, s_in_radius, s_npts, s_nplan, s_shot_coll, s_shot_bad;
   __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls;
@@ -598,7 +607,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
     int32_t *hql = P.hq_log ? P.hq_log + (size_t)sc * AVP_HQ_CAP * 3 : nullptr;
     int *dbg = P.dbg ? P.dbg + (size_t)sc * 8 : nullptr;
     const long long t_start = clock64();
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
+    long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
 #define AVP_TICK(k) do { if (tid == 0) { const long long t_ = clock64(); pc[k] += t_ - tp; tp = t_; } } while (0)
 
     // ---- per-scenario initialisation (all threads)
@@ -626,7 +635,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
         s_nhq++;
         if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
         Node r; r.x = S.pose[0]; r.y = S.pose[1]; r.theta = pi_2_pi(S.pose[2]); r.f = 0; r.g = 0; r.h = 0; r.parent = -1;
-        r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0; r.pad1 = 0;
+        r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0;
+        r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
         { int n_ = s_on; oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
@@ -650,9 +660,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
           s_cur = ret;
           if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
           s_npops++;
-          const Node &cn = nodes[ret];
-          const double distance = sqrt(d_pow2(cn.x - goal[0]) + d_pow2(cn.y - goal[1]));   // hybrid_a_star.py:308-309
-          s_in_radius = distance < cfg.flag_radius;
+          s_in_radius = nodes[ret].in_radius;
           s_shot_coll = 0; s_shot_bad = 0; s_npts = 0; s_nplan = 0; s_best.ok = 0;
           s_ctl = CTL_RUN;
         }
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
 
       // phase 0: successor poses and the normalised rs queries (threads 32.. so that thread 0 can
       //          finish heapq.heappop meanwhile: move the last entry to the root, sift)
-      if (tid == 0) { int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; }
+      if (tid == 0) { const long long t_ = clock64(); int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; pc[13] += clock64() - t_; pc[14] += n_; }
       {
         const int t0 = (BLOCK >= 64) ? 32 : 0;       // keep thread 0's warp free for the heap
         const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
@@ -851,7 +859,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
             n.g = s_coll[i] ? 0.0 : node_cost(cfg, fwd, n.theta, cn.theta, cn.forward != 0);    // :206-209
             n.f = 0; n.h = 0;
             n.forward = fwd ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); n.in_open = 0;
-            n.in_closed = s_coll[i] ? 1 : 0; n.hpos = -1; n.pad1 = 0;
+            n.in_closed = s_coll[i] ? 1 : 0; n.hpos = -1;
+            n.in_radius = s_coll[i] ? 0 : (sqrt(d_pow2(n.x - goal[0]) + d_pow2(n.y - goal[1])) < cfg.flag_radius);
             nodes[child] = n;
             s_g[i] = n.g;
             __threadfence_block();
@@ -866,6 +875,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
           if (!s_rsok[i]) s_status = AVP_RS_DEGENERATE;
           const long long id = map_index(S, s_cpose[i][0], s_cpose[i][1]);                 // calc_node_heuristic (:261-283)
           s_hv[i] = (id >= 0 && id < S.n_ids) ? hval[id] : -1;
+          s_h1[i] = s_hv[i] / 100.0;                                                      // h_value_1 / 100 (:295)
         }
       }
       __syncthreads();
@@ -884,13 +894,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
               if (s_skip[i]) continue;
               if (s_found[i] < 0 && s_coll[i]) { s_nclosed++; continue; }
               int hv = s_hv[i];
+              double h1 = s_h1[i];
               if (n_miss > 0) {                    // a Dijkstra resume since the prefetch: re-read the table
                 const long long id = map_index(S, s_cpose[i][0], s_cpose[i][1]);
                 hv = (id >= 0 && id < S.n_ids) ? hval[id] : -1;
+                h1 = hv / 100.0;
               }
               if (hv < 0) break;                   // miss: needs the warp
               s_nhcalls++;
-              const double h1 = hv / 100.0, h2 = s_rsL[i];
+              const double h2 = s_rsL[i];
               const double h = (h2 > h1) ? h2 : h1;                       // max(h_value_1, h_value_2) (:294-296)
               const int found = s_found[i];
               if (found < 0) {                                            // :206-216
@@ -898,7 +910,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
                 Node &n = nodes[child];
                 const double f = s_g[i] + h;
                 n.h = h; n.f = f; n.in_open = 1;
-                oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, on, f, child);
+                { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; pc[12] += nodes[child].hpos; }
               } else {                                                    // :219-230 (in place, no re-heapify)
                 const double new_f = h + s_g[i];
                 if (new_f < s_oldf[i]) {
@@ -914,7 +926,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
           if (stop >= nchild) break;
           // heuristic miss for successor `stop`: Dijkstra.compute_path resumes (compute_h.py:198-214)
           long long term;
+          const long long td_ = clock64();
           const int d = dij_compute_path(s_D, s_heap, s_cpose[stop][0], s_cpose[stop][1], &term);
+          if (lane == 0) { pc[10] += clock64() - td_; pc[11]++; }
           ++n_miss;
           if (lane == 0) {
             if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
@@ -967,7 +981,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
         for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = rs_ct_names[s_best.ct][i];
       }
       if (dbg) dbg[0] = 9;
-      if (P.prof) for (int k = 0; k < 8; ++k) P.prof[(size_t)sc * 8 + k] = pc[k];
+      if (P.prof) for (int k = 0; k < 16; ++k) P.prof[(size_t)sc * 16 + k] = pc[k];
     }
     __syncthreads();
   }

@@ -195,7 +195,7 @@ int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_pass2, int32
  * AVP_HOST_TIMEOUT_S bounds the host's wait for the search kernel. */
 int avp_set_watchdog(avp_ctx *ctx, long long cycles);
 int avp_fetch_debug(avp_ctx *ctx, int32_t *out8n);
-/* per-scenario SM-cycle accumulators of the search kernel's phases (8 int64 each, see avp_api.cu) */
+/* per-scenario SM-cycle accumulators / counters of the search kernel (16 int64 each, see avp_api.cu) */
 int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n);
 
 #ifdef __cplusplus

@@ -23,4 +23,8 @@ for nm, idx in (('long(20000 pops)', long_), ('short', short)):
     print(nm, 'n', len(idx), 'mean pops', pops.mean(), 'total cycles/scenario %.3g' % p.sum(1).mean())
     for k, n in enumerate(names):
         print('   %-16s %10.0f cycles/pop  (%.1f%%)' % (n, (p[:, k] / pops).mean(), 100 * p[:, k].sum() / p.sum()))
+if len(long_):
+    p = pr[long_].astype(np.float64); pops = s['n_pops'][long_].astype(np.float64)
+    print('long: push cycles/pop %.0f  pushes/pop %.2f  cycles/push %.0f  mean final heap pos %.0f  mean heap size %.0f' % ((p[:,8]/pops).mean(), (p[:,9]/pops).mean(), p[:,8].sum()/p[:,9].sum(), p[:,12].sum()/p[:,9].sum(), p[:,14].sum()/pops.sum()))
+    print('long: dijkstra-in-commit cycles/pop %.0f  resumes/scenario %.1f  heappop cycles/pop %.0f' % ((p[:,10]/pops).mean(), p[:,11].mean(), (p[:,13]/pops).mean()))
 print('h_closed mean', s['h_closed'].mean(), 'n_hq mean', s['n_hq'].mean())
