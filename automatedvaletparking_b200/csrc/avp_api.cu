@@ -7,6 +7,8 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <utility>
 #include <time.h>
 #include "avp_kernels.cuh"
 
@@ -33,6 +35,7 @@ struct avp_ctx {
   int ws_slots = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
   Node *d_nodes = nullptr; int32_t *d_oheap = nullptr, *d_htab = nullptr; unsigned long long *d_dheap = nullptr; double *d_oheap_f = nullptr;
   int slots_wide = 0; int slots_w[3] = {0, 0, 0}; int32_t *d_worklist = nullptr; int worklist_cap = 0;
+  int32_t *d_order = nullptr;      // pass-1 processing order: expensive scenarios (far start-goal pairs) first
   double *d_course = nullptr; int32_t *d_course_dir = nullptr;
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
@@ -114,6 +117,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
   free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_worklist);
+  free_dev(ctx->d_order);
   free_dev(ctx->d_dq_save); free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->evA) cudaEventDestroy(ctx->evA); if (ctx->evB) cudaEventDestroy(ctx->evB);
@@ -156,6 +160,16 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
     S.cost_off = cost_off; cost_off += (int64_t)S.nx * S.ny; cost_off = (cost_off + 15) & ~15ll;
     S.col_off = col_off; col_off += S.nx + 1;
     S.id_off = id_off; id_off += (S.n_ids + 3) & ~3;
+  }
+  {   // longest-first order for the persistent CTAs' work counter (the eager Dijkstra grows with the start-goal distance)
+    std::vector<std::pair<double, int32_t>> key(n);
+    for (int i = 0; i < n; ++i) { const ScenDev &S = ctx->h_scen[i]; const double ddx = S.pose[0] - S.pose[3], ddy = S.pose[1] - S.pose[4]; key[i] = {-(ddx * ddx + ddy * ddy), i}; }
+    std::stable_sort(key.begin(), key.end());
+    std::vector<int32_t> order(n);
+    for (int i = 0; i < n; ++i) order[i] = key[i].second;
+    free_dev(ctx->d_order); ctx->d_order = nullptr;
+    CK(cudaMalloc(&ctx->d_order, sizeof(int32_t) * n));
+    CK(cudaMemcpy(ctx->d_order, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   }
   ctx->n = n; ctx->cost_bytes = cost_off; ctx->col_count = col_off; ctx->id_count = id_off;
   const int n_poly = obs_off[n];
@@ -371,7 +385,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.watchdog_cycles = ctx->watchdog_cycles;
   const char *pb = getenv("AVP_POP_BUDGET");
   const int budget = pb ? atoi(pb) : 1024;
-  P.work_list = nullptr; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
+  P.work_list = ctx->d_order; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));

@@ -149,6 +149,7 @@ struct VehGeom {
   double x_min, x_max, y_min, y_max;
   double v_lb, v_len;
   double lk[4], lb[4], ls[4];   // slope, intercept, sqrt(1+k^2) of the 4 boundary lines
+  double ils[4];                // 1/ls: estimates only (see cell_hits)
 };
 
 __device__ __forceinline__ double shfl_dbl(double v, int src) {
@@ -189,18 +190,34 @@ __device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y
   const double side = sqrt(d0 * d0 + d1 * d1);
   g.v_lb = shfl_dbl(side, 0); g.v_len = shfl_dbl(side, 1);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { g.lk[i] = shfl_dbl(lk, i); g.lb[i] = shfl_dbl(lb, i); g.ls[i] = shfl_dbl(ls, i); }
+  const double ils = 1.0 / ls;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { g.lk[i] = shfl_dbl(lk, i); g.lb[i] = shfl_dbl(lb, i); g.ls[i] = shfl_dbl(ls, i); g.ils[i] = shfl_dbl(ils, i); }
 }
 
-// the per-cell predicate of distance_checker.check (collision_check.py:197-238)
+// the per-cell predicate of distance_checker.check (collision_check.py:197-238).
+// Exact, but division-free in the common case: every quotient the reference forms is first
+// estimated with a reciprocal / a product; the true IEEE division is only evaluated when the
+// estimate is too close to the decision threshold to be trusted (|margin| < 1e-9).
 __device__ __forceinline__ bool cell_hits(const VehGeom &g, double ox, double oy) {
-  double dis[4];
+  // dis_i = |k_i*x + b_i - y| / sqrt(1 + k_i^2)   (collision_check.py:158-160)
+  double num[4], est[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dis[i] = fabs(g.lk[i] * ox + g.lb[i] - oy) / g.ls[i];
-  const bool c1 = fabs(dis[0] - dis[2]) < g.v_lb - 0.01;
-  const bool c2 = fabs(dis[1] - dis[3]) < g.v_len - 0.01;
+  for (int i = 0; i < 4; ++i) { num[i] = fabs(g.lk[i] * ox + g.lb[i] - oy); est[i] = num[i] * g.ils[i]; }
+  const double t1 = g.v_lb - 0.01, t2 = g.v_len - 0.01;
+  const double m1 = fabs(est[0] - est[2]) - t1, m2 = fabs(est[1] - est[3]) - t2;
+  bool c1, c2;
+  const bool sure = (fabs(m1) > 1e-9) && (fabs(m2) > 1e-9) && (est[0] < 1e4) && (est[1] < 1e4) && (est[2] < 1e4) && (est[3] < 1e4);
+  if (sure) { c1 = m1 < 0.0; c2 = m2 < 0.0; }
+  else {                                   // near a threshold, or inf/nan slopes: the reference's own arithmetic
+    double dis[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dis[i] = num[i] / g.ls[i];
+    c1 = fabs(dis[0] - dis[2]) < t1;                                    // :202
+    c2 = fabs(dis[1] - dis[3]) < t2;                                    // :203
+  }
   if (c1 && c2) return true;
-  bool on_x = false, on_y = false;
+  bool on_x = false, on_y = false;                                      // :210-230
 #pragma unroll
   for (int i = 0; i < 5; ++i) on_x |= (ox == g.vb[i][0]);
   if (on_x) {
@@ -209,9 +226,13 @@ __device__ __forceinline__ bool cell_hits(const VehGeom &g, double ox, double oy
   }
   if (on_x && on_y) return true;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const double k1 = (g.vb[i][1] - oy) / (g.vb[i][0] - ox);
-    if (k1 == g.lk[i]) return true;
+  for (int i = 0; i < 4; ++i) {                                         // :233-238: k1 == line_k[i]
+    const double a = g.vb[i][1] - oy, d = g.vb[i][0] - ox, t = g.lk[i] * d;
+    // fl(a/d) == lk needs a ~ lk*d to ~1e-15 relative; skip the division when they differ by far more
+    if (fabs(a - t) <= 1e-9 * (fabs(a) + fabs(t)) || !(fabs(a) < 1e300) || !(fabs(t) < 1e300) || d == 0.0) {
+      const double k1 = a / d;
+      if (k1 == g.lk[i]) return true;
+    }
   }
   return false;
 }

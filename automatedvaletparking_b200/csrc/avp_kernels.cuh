@@ -673,9 +673,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       const Node cn = nodes[cur];
       const int phi_np = cur != 0;           // root theta is a Python float (see oracle generate_path)
 
-      // phase 0: successor poses and the normalised rs queries (threads 32.. so that thread 0 can
-      //          finish heapq.heappop meanwhile: move the last entry to the root, sift)
-      if (tid == 0) { const long long t_ = clock64(); int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; pc[13] += clock64() - t_; pc[14] += n_; }
+      // phase 0: successor poses and the normalised rs queries (threads 32..)
       {
         const int t0 = (BLOCK >= 64) ? 32 : 0;       // keep thread 0's warp free for the heap
         const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
@@ -703,7 +701,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       // (speculative for successors that turn out skipped / colliding)
       // item = inst * (nchild + 1) + row: the lanes of a warp evaluate the SAME word formula for different
       // poses (instances of one family are adjacent), instead of 32 different formulas
-      for (int item = tid; item < (nchild + 1) * RS_NINST; item += BLOCK) {
+      // Thread 0 takes no item when the CTA is wide enough: it finishes heapq.heappop meanwhile (move the
+      // last entry to the root, sift) -- nothing in phases 1-4 touches the open heap.
+      constexpr int RS_T0 = (BLOCK >= 512) ? 1 : 0;
+      if (tid == 0) { const long long t_ = clock64(); int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; pc[13] += clock64() - t_; pc[14] += n_; }
+      for (int item = tid - RS_T0; item >= 0 && item < (nchild + 1) * RS_NINST; item += BLOCK - RS_T0) {
         const int inst = item / (nchild + 1), row = item - inst * (nchild + 1);
         if (row == nchild && !s_in_radius) continue;
         double t, u, v;
