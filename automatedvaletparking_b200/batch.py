@@ -252,6 +252,11 @@ class DevicePlanner:
         self._ck(self._L.avp_fetch_profile(self._h, out.ctypes.data_as(_native.c_lp)), "avp_fetch_profile")
         return out
 
+    def warp_profile(self) -> np.ndarray:
+        out = np.zeros((self.n, 16, 8), dtype=np.int64)
+        self._ck(self._L.avp_fetch_warp_profile(self._h, out.ctypes.data_as(_native.c_lp)), "avp_fetch_warp_profile")
+        return out
+
     def set_watchdog(self, cycles: int):
         self._ck(self._L.avp_set_watchdog(self._h, int(cycles)), "avp_set_watchdog")
 

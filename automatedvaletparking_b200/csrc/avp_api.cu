@@ -11,6 +11,7 @@
 #include <utility>
 #include <time.h>
 #include "avp_kernels.cuh"
+#include "avp_search_pipe.cuh"
 
 struct avp_ctx {
   int device = 0;
@@ -28,11 +29,15 @@ struct avp_ctx {
   int32_t *d_col = nullptr; int64_t col_count = 0;
   double2 *d_cells = nullptr; int64_t cell_count = 0;
   bool rasterised = false;
+  // byte capacities of the scenario arrays: uploads of a same-sized batch reuse the allocations (cudaMalloc/cudaFree are
+  // synchronising and cost far more than the H2D copies of a batch)
+  size_t cap_scen = 0, cap_nv = 0, cap_vert_off = 0, cap_verts = 0, cap_cost = 0, cap_col = 0, cap_cells = 0, cap_ids = 0, cap_order = 0;
   // per-id arrays
   int64_t id_count = 0;
   int32_t *d_hval = nullptr, *d_ost = nullptr; double *d_gx = nullptr, *d_gy = nullptr;
   // per-slot workspaces
   int ws_slots = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
+  NodeShot *d_nshot = nullptr; int nshot_slots = 0, nshot_node_cap = 0;   // pipelined pass-2 kernel only
   Node *d_nodes = nullptr; int32_t *d_oheap = nullptr, *d_htab = nullptr; unsigned long long *d_dheap = nullptr; double *d_oheap_f = nullptr;
   int slots_wide = 0; int slots_w[3] = {0, 0, 0}; int32_t *d_worklist = nullptr; int worklist_cap = 0;
   int32_t *d_order = nullptr;      // pass-1 processing order: expensive scenarios (far start-goal pairs) first
@@ -40,7 +45,7 @@ struct avp_ctx {
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
-  long long *d_prof = nullptr;
+  long long *d_prof = nullptr, *d_wprof = nullptr;
   int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
   float pass_ms[2] = {0.f, 0.f}; int n_pending = 0; int wide_block = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -54,6 +59,17 @@ struct avp_ctx {
 #define FAIL(msg) do { ctx->err = (msg); return -2; } while (0)
 
 static void free_dev(void *p) { if (p) cudaFree(p); }
+
+// grow-only device buffer: reallocates when `bytes` exceeds the capacity (or is far below it)
+template <class T>
+static cudaError_t ensure_dev(T **p, size_t *cap, size_t bytes) {
+  if (*p && bytes <= *cap && bytes * 4 >= *cap) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 16);
+  if (e == cudaSuccess) *cap = bytes ? bytes : 16;
+  return e;
+}
 
 static int ensure_scratch(avp_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->scratch_bytes) return 0;
@@ -89,6 +105,9 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   ctx->slots_w[1] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<256>, 256, 12 * avp_sm_open(256)) == cudaSuccess && o > 0) ? o : 1);
   ctx->slots_w[2] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<128>, 128, 12 * avp_sm_open(128)) == cudaSuccess && o > 0) ? o : 1);
   ctx->slots_wide = ctx->slots_w[0];
+  cudaFuncSetAttribute(k_search_pipe<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
+  cudaFuncSetAttribute(k_search_pipe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
+  cudaFuncSetAttribute(k_search_pipe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(128));
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
   *out = ctx;
@@ -100,13 +119,15 @@ static void free_scenarios(avp_ctx *ctx) {
   free_dev(ctx->d_col); free_dev(ctx->d_cells); free_dev(ctx->d_hval); free_dev(ctx->d_ost); free_dev(ctx->d_gx); free_dev(ctx->d_gy);
   ctx->d_scen = nullptr; ctx->d_nv = ctx->d_vert_off = nullptr; ctx->d_verts = nullptr; ctx->d_cost = nullptr; ctx->d_col = nullptr;
   ctx->d_cells = nullptr; ctx->d_hval = ctx->d_ost = nullptr; ctx->d_gx = ctx->d_gy = nullptr;
+  ctx->cap_scen = ctx->cap_nv = ctx->cap_vert_off = ctx->cap_verts = ctx->cap_cost = ctx->cap_col = ctx->cap_cells = ctx->cap_ids = 0;
   ctx->n = 0; ctx->rasterised = false; ctx->dq_scen = -1;
 }
 static void free_results(avp_ctx *ctx) {
-  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq); free_dev(ctx->d_dbg); ctx->d_dbg = nullptr; free_dev(ctx->d_prof); ctx->d_prof = nullptr;
+  free_dev(ctx->d_sums); free_dev(ctx->d_paths); free_dev(ctx->d_pops); free_dev(ctx->d_hq); free_dev(ctx->d_dbg); ctx->d_dbg = nullptr; free_dev(ctx->d_prof); ctx->d_prof = nullptr; free_dev(ctx->d_wprof); ctx->d_wprof = nullptr;
   ctx->d_sums = nullptr; ctx->d_paths = nullptr; ctx->d_pops = nullptr; ctx->d_hq = nullptr; ctx->res_n = 0;
 }
 static void free_ws(avp_ctx *ctx) {
+  free_dev(ctx->d_nshot); ctx->d_nshot = nullptr; ctx->nshot_slots = 0; ctx->nshot_node_cap = 0;
   free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir); free_dev(ctx->d_oheap_f);
   ctx->d_oheap_f = nullptr; ctx->d_nodes = nullptr; ctx->d_oheap = ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
 }
@@ -134,7 +155,7 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
   if (!ctx) return -3;
   if (n <= 0 || !poses || !obs_off) FAIL("avp_scenarios_upload: bad arguments");
   CK(cudaSetDevice(ctx->device));
-  free_scenarios(ctx);
+  ctx->n = 0; ctx->rasterised = false; ctx->dq_scen = -1;
   const double ds = ctx->cfg.map_discrete_size;
   ctx->h_scen.assign(n, ScenDev());
   int64_t cost_off = 0, col_off = 0, id_off = 0;
@@ -167,23 +188,27 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
     std::stable_sort(key.begin(), key.end());
     std::vector<int32_t> order(n);
     for (int i = 0; i < n; ++i) order[i] = key[i].second;
-    free_dev(ctx->d_order); ctx->d_order = nullptr;
-    CK(cudaMalloc(&ctx->d_order, sizeof(int32_t) * n));
+    CK(ensure_dev(&ctx->d_order, &ctx->cap_order, sizeof(int32_t) * n));
     CK(cudaMemcpy(ctx->d_order, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   }
   ctx->n = n; ctx->cost_bytes = cost_off; ctx->col_count = col_off; ctx->id_count = id_off;
   const int n_poly = obs_off[n];
   const int n_vert = n_poly > 0 ? vert_off[n_poly] : 0;
-  CK(cudaMalloc(&ctx->d_scen, sizeof(ScenDev) * n));
-  CK(cudaMalloc(&ctx->d_nv, sizeof(int32_t) * (n_poly + 1)));
-  CK(cudaMalloc(&ctx->d_vert_off, sizeof(int32_t) * (n_poly + 1)));
-  CK(cudaMalloc(&ctx->d_verts, sizeof(double) * 2 * (n_vert + 1)));
-  CK(cudaMalloc(&ctx->d_cost, (size_t)cost_off + 16));
-  CK(cudaMalloc(&ctx->d_col, sizeof(int32_t) * (col_off + 1)));
-  CK(cudaMalloc(&ctx->d_hval, sizeof(int32_t) * id_off));
-  CK(cudaMalloc(&ctx->d_ost, sizeof(int32_t) * id_off));
-  CK(cudaMalloc(&ctx->d_gx, sizeof(double) * id_off));
-  CK(cudaMalloc(&ctx->d_gy, sizeof(double) * id_off));
+  CK(ensure_dev(&ctx->d_scen, &ctx->cap_scen, sizeof(ScenDev) * n));
+  CK(ensure_dev(&ctx->d_nv, &ctx->cap_nv, sizeof(int32_t) * (n_poly + 1)));
+  CK(ensure_dev(&ctx->d_vert_off, &ctx->cap_vert_off, sizeof(int32_t) * (n_poly + 1)));
+  CK(ensure_dev(&ctx->d_verts, &ctx->cap_verts, sizeof(double) * 2 * (n_vert + 1)));
+  CK(ensure_dev(&ctx->d_cost, &ctx->cap_cost, (size_t)cost_off + 16));
+  CK(ensure_dev(&ctx->d_col, &ctx->cap_col, sizeof(int32_t) * (col_off + 1)));
+  if (!ctx->d_hval || (size_t)id_off > ctx->cap_ids || (size_t)id_off * 4 < ctx->cap_ids) {     // the four per-id arrays share one capacity (entries)
+    free_dev(ctx->d_hval); free_dev(ctx->d_ost); free_dev(ctx->d_gx); free_dev(ctx->d_gy);
+    ctx->d_hval = ctx->d_ost = nullptr; ctx->d_gx = ctx->d_gy = nullptr; ctx->cap_ids = 0;
+    CK(cudaMalloc(&ctx->d_hval, sizeof(int32_t) * id_off));
+    CK(cudaMalloc(&ctx->d_ost, sizeof(int32_t) * id_off));
+    CK(cudaMalloc(&ctx->d_gx, sizeof(double) * id_off));
+    CK(cudaMalloc(&ctx->d_gy, sizeof(double) * id_off));
+    ctx->cap_ids = (size_t)id_off;
+  }
   CK(cudaMemcpyAsync(ctx->d_scen, ctx->h_scen.data(), sizeof(ScenDev) * n, cudaMemcpyHostToDevice, ctx->stream));
   if (n_poly > 0) {
     CK(cudaMemcpyAsync(ctx->d_nv, nv, sizeof(int32_t) * n_poly, cudaMemcpyHostToDevice, ctx->stream));
@@ -208,8 +233,7 @@ extern "C" int avp_rasterise(avp_ctx *ctx) {
   int64_t cell_off = 0;
   for (int i = 0; i < n; ++i) { ScenDev &S = ctx->h_scen[i]; S.cell_off = cell_off; S.cell_cap = S.n_obs; cell_off += (S.n_obs + 1) & ~1; }
   ctx->cell_count = cell_off;
-  free_dev(ctx->d_cells); ctx->d_cells = nullptr;
-  CK(cudaMalloc(&ctx->d_cells, sizeof(double2) * (cell_off + 1)));
+  CK(ensure_dev(&ctx->d_cells, &ctx->cap_cells, sizeof(double2) * (cell_off + 1)));
   CK(cudaMemcpyAsync(ctx->d_scen, ctx->h_scen.data(), sizeof(ScenDev) * n, cudaMemcpyHostToDevice, ctx->stream));
   k_fill_cells<<<n, 128, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_cost, ctx->d_col, ctx->d_cells); ctx->launches++;
   CK(cudaGetLastError());
@@ -334,6 +358,8 @@ static int ensure_results(avp_ctx *ctx, int cap_path, int cap_pops) {
   CK(cudaMalloc(&ctx->d_dbg, sizeof(int) * n * 8));
   CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * n * 16));
   CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * n * 16));
+  CK(cudaMalloc(&ctx->d_wprof, sizeof(long long) * n * 128));
+  CK(cudaMemset(ctx->d_wprof, 0, sizeof(long long) * n * 128));
   CK(cudaMemset(ctx->d_dbg, 0, sizeof(int) * n * 8));
   ctx->res_n = ctx->n; ctx->cap_path = cap_path; ctx->cap_pops = cap_pops;
   return 0;
@@ -382,7 +408,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.oheap_f = ctx->d_oheap_f;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
-  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.watchdog_cycles = ctx->watchdog_cycles;
+  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof; P.watchdog_cycles = ctx->watchdog_cycles;
   const char *pb = getenv("AVP_POP_BUDGET");
   const int budget = pb ? atoi(pb) : 1024;
   P.work_list = ctx->d_order; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
@@ -417,8 +443,21 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       int cap = which < 3 ? ctx->slots_w[which] : ctx->slots;
       int grid2 = cap; if (grid2 > npend) grid2 = npend; if (grid2 > ctx->ws_slots) grid2 = ctx->ws_slots;
       ctx->wide_block = which == 0 ? 512 : which == 1 ? 256 : which == 2 ? 128 : AVP_BLOCK_NARROW;
+      // pass 2 runs the pipelined kernel (avp_search_pipe.cuh); AVP_PIPE=0 selects the phase-sequential k_search (A/B runs)
+      const char *pe = getenv("AVP_PIPE");
+      const bool pipe = which < 3 && !(pe && atoi(pe) == 0);
+      if (pipe && (ctx->nshot_slots < grid2 || ctx->nshot_node_cap != ctx->node_cap)) {
+        free_dev(ctx->d_nshot); ctx->d_nshot = nullptr; ctx->nshot_slots = 0;
+        const int ns = std::max(grid2, std::min(ctx->ws_slots, ctx->slots_w[0]));
+        CK(cudaMalloc(&ctx->d_nshot, sizeof(NodeShot) * (size_t)ns * ctx->node_cap));
+        ctx->nshot_slots = ns; ctx->nshot_node_cap = ctx->node_cap;
+      }
+      P.nshot = ctx->d_nshot;
       CK(cudaEventRecord(ctx->ev0, ctx->stream));
-      if (which == 0) k_search<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
+      if (pipe && which == 0) k_search_pipe<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
+      else if (pipe && which == 1) k_search_pipe<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
+      else if (pipe && which == 2) k_search_pipe<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
+      else if (which == 0) k_search<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
       else if (which == 1) k_search<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
       else if (which == 2) k_search<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
       else k_search<AVP_BLOCK_NARROW><<<grid2, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW), ctx->stream>>>(P);
@@ -554,6 +593,14 @@ extern "C" int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_p
  * rs instances, [4] selection + course plan, [5] course + shot check, [6] commit, [7] commit preparation,
  * [8] cycles in open-heap pushes, [9] pushes, [10] cycles in Dijkstra resumes during commits, [11] resumes,
  * [12] sum of final heap positions of pushed nodes, [13] cycles in heappop, [14] sum of heap sizes at pops */
+extern "C" int avp_fetch_warp_profile(avp_ctx *ctx, int64_t *out128n) {
+  if (!ctx || !out128n) return -3;
+  if (!ctx->d_wprof) FAIL("avp_fetch_warp_profile: no results");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(out128n, ctx->d_wprof, sizeof(long long) * (size_t)ctx->n * 128, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n) {
   if (!ctx) return -3;
   if (!ctx->d_prof) FAIL("avp_fetch_profile: no results");

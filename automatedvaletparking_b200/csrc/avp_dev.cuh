@@ -485,7 +485,7 @@ __device__ __forceinline__ int rs_arrange(int inst, double t, double u, double v
 // set_path / calc_optimal_path semantics (rs_curve.py:137-156, :99-110).
 struct RsCand { double t, u, v, L; };   // L = sum(|lengths|) of the arranged word (rs_curve.py:148)
 
-struct RsBest { int ok; int degenerate; int n; int ct; double len[5]; double L; /* normalised */ };
+struct RsBest { int ok; int degenerate; int n; int ct; double len[5]; double L; /* normalised */ int inst; /* winning word instance */ };
 
 // instances that can share a ctype form 11 groups (same family pair), in instance order
 __device__ __constant__ int8_t rs_grp_begin[12] = {0, 1, 2, 6, 10, 18, 26, 30, 34, 38, 42, 46};
@@ -531,7 +531,7 @@ __device__ __forceinline__ void rs_select_group(const RsCand *cand, unsigned lon
 
 // combine the group winners in order (equivalent to the sequential scan over all retained words)
 __device__ __forceinline__ void rs_combine_groups(const RsGroupBest *gb, const RsCand *cand, int xy_np, int phi_np, RsBest &best) {
-  best.ok = 0; best.degenerate = 0;
+  best.ok = 0; best.degenerate = 0; best.inst = -1;
   int bi = -1; double minL = 0.0;
   for (int g = 0; g < RS_NGROUP; ++g) {
     best.degenerate |= gb[g].degenerate;
@@ -541,7 +541,7 @@ __device__ __forceinline__ void rs_combine_groups(const RsGroupBest *gb, const R
   if (bi >= 0) {
     unsigned mask;
     best.ok = 1; best.n = rs_arrange(bi, cand[bi].t, cand[bi].u, cand[bi].v, xy_np, phi_np, best.len, best.ct, mask);
-    best.L = cand[bi].L;
+    best.L = cand[bi].L; best.inst = bi;
   }
 }
 

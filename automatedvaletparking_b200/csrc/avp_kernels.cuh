@@ -37,6 +37,11 @@ struct __align__(16) Node {
 };
 static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
 
+// The rs word selected by calc_optimal_path(pose -> goal) when a node was scored (calc_node_heuristic,
+// hybrid_a_star.py:286-292).  try_rs_curve (:326-332) repeats exactly that call when the node is popped,
+// so the pipelined search kernel keeps the word instead of solving it again.
+struct __align__(8) NodeShot { double t, u, v, L; int32_t inst; int32_t ok; };
+
 struct KParams {
   avp_config cfg;
   int n_scen;
@@ -51,6 +56,7 @@ struct KParams {
   // per-slot (persistent CTA) workspaces
   unsigned long long *dheap; int dheap_cap;
   Node *nodes; int node_cap;
+  NodeShot *nshot;                // node_cap per slot (pipelined kernel only)
   double *oheap_f;                // open heap keys beyond the shared-memory part (node_cap per slot)
   int32_t *oheap;                 // open heap node indices beyond the shared-memory part
   int32_t *htab; int htab_size;   // power of two
@@ -66,6 +72,7 @@ struct KParams {
   int n_work;
   int pop_budget;                 // pass 1: a scenario still searching after this many pops ends AVP_PENDING
   long long *prof;                // n * 16 SM-cycle accumulators / counters per scenario (thread 0): phases of the main loop, may be NULL
+  long long *wprof;               // n * 128: per warp (16) and phase (8) work cycles of the pipelined kernel, may be NULL
   int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
   long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY
 };
@@ -334,23 +341,23 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
       long long xi = qx - 1, yi = floor_div_exact(ngy - b2, dy, inv_dy) - 1;
       if (xi >= mx) xi = mx - 1; if (yi >= my) yi = my - 1;
       if (xi < 0) xi += nx; if (yi < 0) yi += ny;             // python negative indexing
-      bool obstacle = false;
-      if (xi >= 0 && xi < nx && yi >= 0 && yi < ny) obstacle = cost[(size_t)xi * ny + yi] == 255;
-      if (!obstacle) {
+      const bool in_map = xi >= 0 && xi < nx && yi >= 0 && yi < ny;
+      const long long id = qx + floor_div_exact(b3 - ngy, dy, inv_dy) * (long long)stride;   // costmap.py:319-329
+      const bool id_ok = id >= 0 && id < n_ids;
+      // both loads are issued before either result is needed (one memory round trip instead of two)
+      const uint8_t cv = in_map ? cost[(size_t)xi * ny + yi] : (uint8_t)0;
+      const int st = id_ok ? ost[(int)id] : -3;
+      if (cv != 255) {
         bool ok = true;
         if (ddx < 0 && !(ngx >= b0)) ok = false; if (ddx > 0 && !(ngx <= b1)) ok = false;
         if (ddy > 0 && !(ngy <= b3)) ok = false; if (ddy < 0 && !(ngy >= b2)) ok = false;
-        if (ok) {
-          const long long id = qx + floor_div_exact(b3 - ngy, dy, inv_dy) * (long long)stride;   // costmap.py:319-329
-          if (id >= 0 && id < n_ids) {
-            nid = (int)id;
-            const int st = ost[nid];
-            prio = cur_dist + ((ddx && ddy) ? 14 : 10);
-            key = ((unsigned long long)(unsigned)prio << 32) | (unsigned)nid;
-            if (st == -1) {                    // first visit (add_grid_to_openlist :229-235): this lane records the Grid
-              action = 1; ost[nid] = prio; gxa[nid] = ngx; gya[nid] = ngy;
-            } else if (st >= 0 && st > prio) action = 2;      // queued with a larger distance (:222-228)
-          }
+        if (ok && id_ok) {
+          nid = (int)id;
+          prio = cur_dist + ((ddx && ddy) ? 14 : 10);
+          key = ((unsigned long long)(unsigned)prio << 32) | (unsigned)nid;
+          if (st == -1) {                    // first visit (add_grid_to_openlist :229-235): this lane records the Grid
+            action = 1; ost[nid] = prio; gxa[nid] = ngx; gya[nid] = ngy;
+          } else if (st >= 0 && st > prio) action = 2;      // queued with a larger distance (:222-228)
         }
       }
     }
@@ -413,7 +420,10 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
       }
       const int id = (int)(unsigned)top;
       ost[id] = -2;
-      if (hval[id] < 0) hval[id] = (int)(top >> 32);
+      // closedlist: the first entry per id wins (hybrid_a_star.py:272-283).  Only the goal cell is ever closed twice
+      // (initial_map puts it there with distance 0 and a neighbour re-pushes it once), so every other
+      // id is written unconditionally: no load of hval on the pop path
+      if ((long long)id != gid) hval[id] = (int)(top >> 32);
     }
     hn -= 1; closed_len++;
     cur_dist = (int)(top >> 32);

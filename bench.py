@@ -74,7 +74,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.p = index, [], None
+        self.index, self.rows, self.p, self.first = index, [], None, 0
+
+    def mark(self):
+        """samples from here on belong to the timed region (nvidia-smi itself is started before the warm-up:
+        its start-up takes driver locks for a few hundred ms and must not sit inside the timed steps)"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -93,10 +98,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.p.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -204,12 +210,13 @@ def main():
     K = args.steps
 
     # ---------------- resident leg (value): rasterise + search, results stay on the device
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(W):
         dp.rasterise()
         dp.plan_resident(CAP_PATH, 0)
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    clocks.mark()
     l0 = dp.launches
     dp.timer_start()
     search_ms = []

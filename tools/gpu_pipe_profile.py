@@ -1,0 +1,42 @@
+"""Per-phase cycle counters of the pipelined pass-2 kernel (k_search_pipe) on the bench workload.
+Commit warp (thread 0) and evaluators (thread 32) keep separate accumulators (avp_search_pipe.cuh)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+import numpy as np
+import bench
+from automatedvaletparking_b200.batch import DevicePlanner
+os.environ.setdefault('AVP_HOST_TIMEOUT_S', '120')
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+dp = DevicePlanner(max_pops=20000)
+scs = bench.make_scenarios(0, n, dp)
+dp.load(scs)
+ms = dp.plan_resident(256, 0); ms = dp.plan_resident(256, 0)
+res = dp.fetch(256, 0)
+pr = dp.phase_profile()
+s = res.summaries
+print('search ms', ms, 'passes', dp.last_search_passes(), 'successors', res.successors)
+long_ = np.where(s['n_pops'] >= 20000)[0]
+mid = np.where((s['n_pops'] >= 1024) & (s['n_pops'] < 20000))[0]
+names = {0: 'C init+dij0', 1: 'C accept+lookups+predict', 2: 'C commit', 3: 'C heappop', 4: 'C wait for E',
+         7: 'E0 poses+plan', 12: 'E1 rs+points', 13: 'E2 select+collision', 14: 'E3 combine', 15: 'E wait for C'}
+for nm, idx in (('long(20000 pops)', long_), ('mid(1024..20000)', mid)):
+    if len(idx) == 0:
+        continue
+    p = pr[idx].astype(np.float64)
+    pops = s['n_pops'][idx].astype(np.float64)
+    print(nm, 'n', len(idx), 'mean pops', pops.mean())
+    for k in sorted(names):
+        print('   %-28s %10.0f cycles/pop' % (names[k], (p[:, k] / pops).mean()))
+    print('   hits/pop %.4f  misses/pop %.4f' % ((p[:, 5] / pops).mean(), (p[:, 6] / pops).mean()))
+    print('   push cycles/pop %.0f pushes/pop %.2f | dijkstra cycles/pop %.0f resumes/scenario %.1f' %
+          ((p[:, 8] / pops).mean(), (p[:, 9] / pops).mean(), (p[:, 10] / pops).mean(), p[:, 11].mean()))
+    print('   C total/pop %.0f   E total/pop %.0f' % ((p[:, 1:5].sum(1) / pops).mean(), (p[:, [7, 12, 13, 14, 15]].sum(1) / pops).mean()))
+
+wp = dp.warp_profile()
+if len(long_):
+    w = wp[long_].astype(np.float64) / s['n_pops'][long_].astype(np.float64)[:, None, None]
+    w = w.mean(0)
+    print('per-warp WORK cycles/pop (long scenarios): E0 E1 E2 E3 | plan:arrange increments planloop | select')
+    for k in range(16):
+        print('  warp %2d  %7.0f %7.0f %7.0f %7.0f | %7.0f %7.0f %7.0f | %7.0f' % (k, w[k, 0], w[k, 1], w[k, 2], w[k, 3], w[k, 4], w[k, 5], w[k, 6], w[k, 7]))
