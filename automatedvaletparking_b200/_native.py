@@ -9,7 +9,7 @@ import os
 from .hostcfg import AvpConfig, AvpPlanSummary
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavp_b200.so")
+LIB_PATH = os.environ.get("AVP_B200_LIB") or os.path.join(_HERE, "libavp_b200.so")     # env override: A/B builds (development aid)
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int32)

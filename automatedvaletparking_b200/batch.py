@@ -253,7 +253,7 @@ class DevicePlanner:
         return out
 
     def warp_profile(self) -> np.ndarray:
-        out = np.zeros((self.n, 16, 8), dtype=np.int64)
+        out = np.zeros((self.n, 16, 24), dtype=np.int64)
         self._ck(self._L.avp_fetch_warp_profile(self._h, out.ctypes.data_as(_native.c_lp)), "avp_fetch_warp_profile")
         return out
 

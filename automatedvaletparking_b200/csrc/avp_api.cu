@@ -108,6 +108,7 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   cudaFuncSetAttribute(k_search_pipe<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
   cudaFuncSetAttribute(k_search_pipe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
   cudaFuncSetAttribute(k_search_pipe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(128));
+  cudaFuncSetAttribute(k_search_pipe2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
   *out = ctx;
@@ -358,8 +359,8 @@ static int ensure_results(avp_ctx *ctx, int cap_path, int cap_pops) {
   CK(cudaMalloc(&ctx->d_dbg, sizeof(int) * n * 8));
   CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * n * 16));
   CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * n * 16));
-  CK(cudaMalloc(&ctx->d_wprof, sizeof(long long) * n * 128));
-  CK(cudaMemset(ctx->d_wprof, 0, sizeof(long long) * n * 128));
+  CK(cudaMalloc(&ctx->d_wprof, sizeof(long long) * n * 384));
+  CK(cudaMemset(ctx->d_wprof, 0, sizeof(long long) * n * 384));
   CK(cudaMemset(ctx->d_dbg, 0, sizeof(int) * n * 8));
   ctx->res_n = ctx->n; ctx->cap_path = cap_path; ctx->cap_pops = cap_pops;
   return 0;
@@ -408,7 +409,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.oheap_f = ctx->d_oheap_f;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
-  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof; P.watchdog_cycles = ctx->watchdog_cycles;
+  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof; { const char *tpp = getenv("AVP_TRACE_POP"); P.trace_pop = tpp ? atoi(tpp) : -1; } P.watchdog_cycles = ctx->watchdog_cycles;
   const char *pb = getenv("AVP_POP_BUDGET");
   const int budget = pb ? atoi(pb) : 1024;
   P.work_list = ctx->d_order; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
@@ -454,7 +455,15 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       }
       P.nshot = ctx->d_nshot;
       CK(cudaEventRecord(ctx->ev0, ctx->stream));
-      if (pipe && which == 0) k_search_pipe<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
+      // AVP_CLUSTER=1: two-CTA thread-block clusters (one scenario on two SMs, collision work on the second CTA)
+      const char *ce = getenv("AVP_CLUSTER");
+      const bool use_cluster = pipe && which == 0 && (ce && atoi(ce) == 1) && ctx->n_sm >= 2;      // opt-in: measured no faster than one CTA (profiles/README.md)
+      if (use_cluster) {
+        int ncl = ctx->n_sm / 2; if (ncl > npend) ncl = npend; if (ncl > ctx->ws_slots) ncl = ctx->ws_slots;
+        ctx->wide_block = 1024;        // reported as 2 x 512
+        k_search_pipe2<512><<<2 * ncl, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
+      }
+      else if (pipe && which == 0) k_search_pipe<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
       else if (pipe && which == 1) k_search_pipe<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
       else if (pipe && which == 2) k_search_pipe<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
       else if (which == 0) k_search<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
@@ -597,7 +606,7 @@ extern "C" int avp_fetch_warp_profile(avp_ctx *ctx, int64_t *out128n) {
   if (!ctx || !out128n) return -3;
   if (!ctx->d_wprof) FAIL("avp_fetch_warp_profile: no results");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(out128n, ctx->d_wprof, sizeof(long long) * (size_t)ctx->n * 128, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out128n, ctx->d_wprof, sizeof(long long) * (size_t)ctx->n * 384, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -72,7 +72,8 @@ struct KParams {
   int n_work;
   int pop_budget;                 // pass 1: a scenario still searching after this many pops ends AVP_PENDING
   long long *prof;                // n * 16 SM-cycle accumulators / counters per scenario (thread 0): phases of the main loop, may be NULL
-  long long *wprof;               // n * 128: per warp (16) and phase (8) work cycles of the pipelined kernel, may be NULL
+  int trace_pop;                  // pipelined kernel: the pop whose per-warp timeline is recorded in wprof (development aid)
+  long long *wprof;               // n * 16 * 24: per warp (16) and phase (8) work cycles of the pipelined kernel, may be NULL
   int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
   long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY
 };

@@ -28,9 +28,20 @@
 // no rs solve; its course is planned while the successor poses are computed and its points are
 // collision-checked in the same queue as the successors' sub-steps.
 #pragma once
+#include <cooperative_groups.h>
 #include "avp_kernels.cuh"
+namespace cg = cooperative_groups;
 
 enum { CTL_FINISH = 2 };
+
+// The rs warp items of the E1 queue: up to three word instances per item (lanes = instance slot x successor), formed so
+// that a warp runs one word formula where possible (4 instances per family: 3 + 1 left over, the left-overs grouped by
+// shared code), and ordered longest first: the tau/omega families (LRLRn 18-21, LRLRp 22-25) as half-size items in front.
+#define RS_NITEM 17
+__device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
+  {18, 19, -1}, {20, 21, -1}, {22, 23, -1}, {24, 25, -1},
+  {6, 7, 8}, {26, 27, 28}, {34, 35, 36}, {42, 43, 44}, {9, 29, 37},
+  {10, 11, 12}, {14, 15, 16}, {45, 13, 17}, {2, 3, 4}, {30, 31, 32}, {38, 39, 40}, {5, 33, 41}, {0, 1, -1}};
 
 struct PureRes {
   double cpose[AVP_NCHILD_MAX][3];
@@ -38,7 +49,7 @@ struct PureRes {
   NodeShot shot[AVP_NCHILD_MAX];
   int32_t coll[AVP_NCHILD_MAX], rsok[AVP_NCHILD_MAX], inrad[AVP_NCHILD_MAX], hid[AVP_NCHILD_MAX];
   int32_t node;                              // the node this result belongs to (-1: none)
-  int32_t in_radius, shot_bad, shot_coll, shot_ok;
+  int32_t in_radius, shot_ok;                // the shot's collision / degeneracy flags stay in shared memory (s_shot_coll, s_shot_bad)
 };
 struct EvalTarget { double x, y, theta; NodeShot shot; int32_t node, in_radius, is_root, valid; };
 
@@ -48,8 +59,13 @@ __device__ __forceinline__ long long clock_ordered() { long long t; asm volatile
 template <int NTHREADS>
 __device__ __forceinline__ void eval_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
+// CLUSTER: the kernel is launched as thread-block clusters of two CTAs (two SMs) per scenario.  CTA 0 is the CTA
+// described above; CTA 1 (the HELPER) takes the collision work of every evaluation -- the successors' sub-step
+// checks and the shot's course (plan, points, checks) -- and writes the flags into CTA 0's shared memory
+// (distributed shared memory); barriers A and B become cluster barriers.  Used when the scenarios of pass 2 fit
+// n_sm / 2 clusters: the evaluation is throughput bound on one SM (see profiles/), two SMs halve it.
+template <int BLOCK, bool CLUSTER>
+__device__ __forceinline__ void search_pipe_body(const KParams &P) {
   static_assert(BLOCK >= 128 && BLOCK % 32 == 0, "one commit warp + at least three evaluator warps");
   constexpr int NWARPS = BLOCK / 32, NE = NWARPS - 1, ET = NE * 32;
   constexpr int SMO = avp_sm_open(BLOCK);
@@ -70,6 +86,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
   __shared__ double s_tcs[2];
   __shared__ double s_g[AVP_NCHILD_MAX], s_oldf[AVP_NCHILD_MAX], s_h1[AVP_NCHILD_MAX];
   __shared__ int s_found[AVP_NCHILD_MAX], s_need[AVP_NCHILD_MAX], s_skip[AVP_NCHILD_MAX], s_hv[AVP_NCHILD_MAX];
+  __shared__ int s_trace_on;
+  __shared__ int s_chit[AVP_NCHILD_MAX];
   __shared__ int s_scen, s_ctlA, s_ctlB, s_cur, s_do_commit, s_rb, s_nplan, s_npts, s_shot_coll, s_shot_bad, s_work;
   __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls, s_on, s_in_radius, s_best_ok;
   __shared__ DijCtx s_D;
@@ -78,7 +96,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
   const avp_config &cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int etid = tid - 32, ewarp = warp - 1;
-  const int slot = blockIdx.x;
+  const int slot = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int rank = CLUSTER ? (int)(blockIdx.x & 1) : 0;          // cluster dims (2,1,1): rank in cluster = blockIdx.x & 1
+  cg::cluster_group cluster = cg::this_cluster();
+#define SYNC_AB() do { if (CLUSTER) cluster.sync(); else __syncthreads(); } while (0)
   const int nchild = 2 * cfg.steering_angle_num;
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
@@ -91,13 +112,152 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
   int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
 
   for (;;) {
-    if (tid == 0) s_scen = atomicAdd(P.work_counter, 1);
-    __syncthreads();
-    if (s_scen >= P.n_work) break;
-    const int sc = P.work_list ? P.work_list[s_scen] : s_scen;
+    if (rank == 0 && tid == 0) s_scen = atomicAdd(P.work_counter, 1);
+    SYNC_AB();
+    const int scen_i = (CLUSTER && rank == 1) ? *cluster.map_shared_rank(&s_scen, 0) : s_scen;
+    if (scen_i >= P.n_work) break;
+    const int sc = P.work_list ? P.work_list[scen_i] : scen_i;
     const ScenDev &S = P.scen[sc];
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
+    if (CLUSTER && rank == 1) {
+      // =========================== HELPER CTA (cluster rank 1) ===========================
+      // Every step: barrier A -> read CTA 0's exit word -> barrier B -> read the target -> sub-step poses ->
+      // one queue: [0] the shot's course plan + points, [1..nchild] one successor's sub-step checks each,
+      // [nchild+1 ..] the course points' checks (they wait for item 0) -> flags to CTA 0's shared memory.
+      const int *r_ctlA = cluster.map_shared_rank(&s_ctlA, 0), *r_ctlB = cluster.map_shared_rank(&s_ctlB, 0);
+      const EvalTarget *r_tgt = cluster.map_shared_rank(&s_tgt, 0);
+      int *r_chit = cluster.map_shared_rank(&s_chit[0], 0), *r_scoll = cluster.map_shared_rank(&s_shot_coll, 0), *r_sbad = cluster.map_shared_rank(&s_shot_bad, 0);
+      for (;;) {
+        cluster.sync();                            // A
+        if (*r_ctlA == CTL_EXIT) break;
+        cluster.sync();                            // B
+        if (*r_ctlB != CTL_RUN) break;
+        if (tid < (int)(sizeof(EvalTarget) / 8)) reinterpret_cast<long long *>(&s_tgt)[tid] = reinterpret_cast<const long long *>(r_tgt)[tid];
+        if (tid == 32) { s_shot_coll = 0; s_shot_bad = 0; s_nplan = 0; s_work = 0; s_npts = -1; }
+        if (tid >= 64 && tid < 64 + nchild) s_chit[tid - 64] = 0;
+        __syncthreads();
+        const EvalTarget T = s_tgt;
+        if (T.valid) {
+          const int phi_np = !T.is_root;
+          const int nsubs = cfg.n_substeps;
+          {
+            const int nsub = nsubs <= 4 ? nsubs : 4;
+            for (int item = warp + NWARPS * lane; item < nchild * nsub; item += NWARPS * 32) {
+              const int i = item / nsub, k = item % nsub;
+              const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+              const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+              const double td_i = speed * cfg.ddt * (k + 1);
+              const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+              const double cs = d_cos(th_i), sn = d_sin(th_i);
+              s_sub[i][k][0] = T.x + td_i * cs; s_sub[i][k][1] = T.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
+            }
+          }
+          __syncthreads();
+          for (;;) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&s_work, 1);
+            it = __shfl_sync(AVP_FULL_MASK, it, 0);
+            if (it == 0) {
+              int npts = 0;
+              if (T.in_radius) {
+                if (lane == 0) {
+                  RsBest b; b.ok = 0; b.degenerate = 0; b.n = 0; b.ct = 0; b.L = 0.0; b.inst = -1;
+                  if (!T.shot.ok) s_shot_bad = 1;
+                  else {
+                    unsigned mask;
+                    b.ok = 1; b.inst = T.shot.inst; b.L = T.shot.L;
+                    b.n = rs_arrange(T.shot.inst, T.shot.t, T.shot.u, T.shot.v, 1, phi_np, b.len, b.ct, mask);
+                    if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
+                  }
+                  s_best = b;
+                  s_tcs[0] = d_cos(-T.theta); s_tcs[1] = d_sin(-T.theta);
+                }
+                __syncwarp();
+                if (!s_shot_bad) {
+                  const int nseg = s_best.n;
+                  const char *mode = rs_ct_names[s_best.ct];
+                  if (lane < nseg) {
+                    double oyaw = 0.0;
+                    for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
+                    double ix, iy, yaw_next = oyaw; int dir;
+                    rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
+                    s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;
+                  }
+                  __syncwarp();
+                  if (lane == 0) {
+                    const double step = 0.5 * maxc;
+                    s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
+                    for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
+                    int ind = 1; double d, pd, ll = 0.0;
+                    CYAW[0] = 0.0; CDIR[0] = -1;
+                    for (int i = 0; i < nseg; ++i) {
+                      const double l = s_best.len[i];
+                      d = (l > 0.0) ? step : -step;
+                      ind -= 1;
+                      if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
+                      while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
+                      if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
+                      ll = l - pd - d;
+                      ind += 1; CYAW[ind] = l; CDIR[ind] = i;
+                    }
+                    s_nplan = ind + 1;
+                  }
+                  __syncwarp();
+                  if (!s_shot_bad) {
+                    const int nplan = s_nplan;
+                    for (int j = lane; j < nplan; j += 32) {
+                      if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
+                      const int seg = CDIR[j]; const double l = CYAW[j];
+                      double px, py, pyaw = 0.0; int dir;
+                      rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
+                      if (mode[seg] == 'S') pyaw = s_org[seg][2];
+                      CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
+                    }
+                    __syncwarp();
+                    if (lane == 0) { int n = nplan; while (n > 0 && CX[n - 1] == 0.0) --n; npts = n; }     // rs_curve.py:588-592
+                  }
+                }
+              }
+              __syncwarp();
+              if (lane == 0) { __threadfence_block(); *(volatile int *)&s_npts = npts; }      // publishes the course: the check items may start
+            } else if (it <= nchild) {
+              const int i = it - 1;
+              int coll = 0;
+              for (int k = 0; k < nsubs; ++k) {
+                bool hit;
+                if (k < 4) hit = check_pose_cs_warp(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3]);
+                else {
+                  const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+                  const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+                  const double td_i = speed * cfg.ddt * (k + 1);
+                  const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+                  hit = check_pose_warp(cfg, S, cells, col_start, T.x + td_i * d_cos(th_i), T.y + td_i * d_sin(th_i), th_i);
+                }
+                if (hit) { coll = 1; break; }
+              }
+              if (lane == 0) s_chit[i] = coll;
+            } else {
+              int npts = 0;
+              if (lane == 0) { while ((npts = *(volatile int *)&s_npts) < 0) __nanosleep(200); }
+              npts = __shfl_sync(AVP_FULL_MASK, npts, 0);
+              const int j = it - 1 - nchild;
+              if (j >= npts) break;
+              const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);
+              if (stop) continue;
+              const double ix = CX[j], iy = CY[j], cm = s_tcs[0], sm = s_tcs[1];
+              const double gx_ = cm * ix + sm * iy + T.x, gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
+              const double gyaw = pi_2_pi(CYAW[j] + T.theta);
+              if (check_pose_warp(cfg, S, cells, col_start, gx_, gy_, pi_2_pi(gyaw))) { if (lane == 0) s_shot_coll = 1; }
+            }
+          }
+        }
+        __syncthreads();
+        if (tid < nchild) r_chit[tid] = s_chit[tid];
+        if (tid == 32) { *r_scoll = s_shot_coll; *r_sbad = s_shot_bad; }
+      }
+      continue;                                    // next scenario
+    }
     int32_t *hval = P.hval + S.id_off, *ost = P.ost + S.id_off;
     const double goal[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
     int32_t *pops = P.pops ? P.pops + (size_t)sc * P.cap_pops : nullptr;
@@ -111,6 +271,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
 #define WP_START() do { if (lane == 0) wt = clock_ordered(); } while (0)
 #define WP_ACC(k) do { if (lane == 0) { const long long t_ = clock_ordered(); s_wp[warp][k] += t_ - wt; wt = t_; } } while (0)
     if (lane == 0) for (int k = 0; k < 8; ++k) s_wp[warp][k] = 0;
+    // timeline of ONE pop (the AVP_TRACE_POP-th of the scenario): absolute clocks of every warp at the phase boundaries
+    long long *tsw = (P.wprof && warp < 16) ? P.wprof + ((size_t)sc * 16 + warp) * 24 + 8 : nullptr;
+#define TS(k) do { __syncwarp(); if (lane == 0 && tsw && ((k) < 2 ? (s_npops == P.trace_pop) : s_trace_on)) tsw[k] = clock_ordered(); } while (0)
 
     // open_list.get() (path_planner.py:70) with the loop's exit tests; lane 0 of the commit warp
     auto do_pop = [&]() {
@@ -179,8 +342,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
 
     bool reached = false;
     for (;;) {
-      __syncthreads();                           // ---- barrier A: the evaluators' result is complete, the next node is popped
+      SYNC_AB();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
       PIPE_TICK(0, 4);                           // commit warp waiting for the evaluators
+      TS(0);
       // s_ctlA is written by do_pop (between B and A) and read here; s_ctlB is written between A and B and read
       // after B: no control word is written while another warp may still be reading it
       if (s_ctlA == CTL_EXIT) break;
@@ -188,62 +352,45 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
         WP_START();
         const int wb = s_rb ^ 1;
         const int cur = s_cur;
-        if (lane == 0) s_ctlB = CTL_RUN;
+        if (lane == 0) { s_ctlB = CTL_RUN; s_trace_on = (s_npops == P.trace_pop); }
         __syncwarp();
         if (s_res[wb].node == cur) {             // the result of the popped node is there
           PureRes &R = s_res[wb];
+          const int shot_bad = R.in_radius ? s_shot_bad : 0, shot_coll = R.in_radius ? s_shot_coll : 0;   // of the evaluation just finished
+          if (lane < nchild) R.coll[lane] = s_chit[lane];          // sub-step collision flags of the evaluation just finished
           if (lane == 0) { s_rb = wb; s_in_radius = R.in_radius; s_best_ok = R.shot_ok; pc[5]++; }
-          if (R.shot_bad) { if (lane == 0) { s_status = (R.shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; s_ctlB = CTL_EXIT; } }
-          else if (R.in_radius && !R.shot_coll) { if (lane == 0) s_ctlB = CTL_FINISH; }     // path_planner.py:86-88
+          __syncwarp();
+          if (shot_bad) { if (lane == 0) { s_status = (shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; s_ctlB = CTL_EXIT; } }
+          else if (R.in_radius && !shot_coll) { if (lane == 0) s_ctlB = CTL_FINISH; }     // path_planner.py:86-88
           else {
-            // ---- lookups, node records, g values, h-table prefetch (hybrid_a_star.py:154-183, :206-222): lanes 0..nchild-1
-            const Node cn = nodes[cur];
-            int found = -1, skip = 1, coll = 0, need = 0;
-            double x_ = 0.0, y_ = 0.0, th = 0.0;
+            // ---- lookups, g values, h-table prefetch (hybrid_a_star.py:154-172, :206-222): lanes 0..nchild-1.
+            //      Node records and table inserts follow after barrier B (the evaluators do not need them).
+            int found = -1, skip = 1, coll = 0;
             if (lane < nchild) {
-              x_ = R.cpose[lane][0]; y_ = R.cpose[lane][1]; th = R.cpose[lane][2];
+              const int i = lane;
+              const int id = R.hid[i];
+              const int hvp = (id >= 0) ? hval[id] : -1;                  // issued first: overlaps the table probes
+              const Node cn = nodes[cur];
+              const double x_ = R.cpose[i][0], y_ = R.cpose[i][1], th = R.cpose[i][2];
               found = htab_find(htab, hmask, nodes, x_, y_, th);
               const bool in_closed = found >= 0 && nodes[found].in_closed;
               const bool oob = (s_nclosed > 0) && (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
               skip = (in_closed || oob) ? 1 : 0;
-              coll = R.coll[lane];
-              need = (!skip) && ((found < 0 && !coll) || (found >= 0));
-              s_found[lane] = found; s_skip[lane] = skip; s_need[lane] = need; s_hv[lane] = -1;
-            }
-            __syncwarp();                        // every lookup precedes every insert
-            if (lane < nchild && !skip) {
-              const int i = lane;
+              coll = R.coll[i];
+              const int need = (!skip) && ((found < 0 && !coll) || (found >= 0));
               const bool fwd = i < nchild / 2.0;
-              if (found < 0) {
-                const int child = s_G + i + 1;
-                if (child >= P.node_cap) s_status = AVP_CAPACITY;
-                else {
-                  Node n; n.x = x_; n.y = y_; n.theta = th; n.parent = cur;
-                  n.g = coll ? 0.0 : node_cost(cfg, fwd, n.theta, cn.theta, cn.forward != 0);    // :206-209
-                  n.f = 0; n.h = 0;
-                  n.forward = fwd ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); n.in_open = 0;
-                  n.in_closed = coll ? 1 : 0; n.hpos = -1;
-                  n.in_radius = coll ? 0 : R.inrad[i];
-                  nodes[child] = n;
-                  if (!coll) nshot[child] = R.shot[i];
-                  s_g[i] = n.g;
-                  __threadfence_block();
-                  htab_insert(htab, hmask, nodes, child);
-                }
-              } else {
-                const Node &n = nodes[found];                                                      // :219-222
-                s_g[i] = node_cost(cfg, n.forward != 0, n.theta, cn.theta, cn.forward != 0);
-                s_oldf[i] = n.f;
+              double g = 0.0;
+              if (!skip) {
+                if (found < 0) g = coll ? 0.0 : node_cost(cfg, fwd, th, cn.theta, cn.forward != 0);           // :206-209
+                else { const Node &n = nodes[found]; g = node_cost(cfg, n.forward != 0, n.theta, cn.theta, cn.forward != 0); s_oldf[i] = n.f; }   // :219-222
               }
-              if (need) {
-                if (!R.rsok[i]) s_status = AVP_RS_DEGENERATE;
-                const int id = R.hid[i];                                                         // calc_node_heuristic (:261-283)
-                s_hv[i] = (id >= 0) ? hval[id] : -1;
-                s_h1[i] = s_hv[i] / 100.0;                                                      // h_value_1 / 100 (:295)
-              }
+              if (need && !R.rsok[i]) s_status = AVP_RS_DEGENERATE;
+              s_found[i] = found; s_skip[i] = skip; s_need[i] = need; s_g[i] = g;
+              s_hv[i] = need ? hvp : -1;                                  // calc_node_heuristic (:261-283)
+              s_h1[i] = s_hv[i] / 100.0;                                  // h_value_1 / 100 (:295)
             }
             __syncwarp();
-            // ---- predict the next open_list.get(): the pushes below put a successor at the root iff its f is
+            // ---- predict the next open_list.get(): the pushes of this commit put a successor at the root iff its f is
             //      below the root's; among successors the first one with the smallest f wins (heapq._siftdown is strict)
             double fc = INFINITY;
             if (lane < nchild && !skip && found < 0 && !coll && s_hv[lane] >= 0) {
@@ -278,13 +425,37 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
       }
       if (warp == 0) WP_ACC(0);
       PIPE_TICK(0, 1);                           // accept + lookups + prediction
-      __syncthreads();                           // ---- barrier B: target published
+      TS(1);
+      SYNC_AB();                                 // ---- barrier B: target published
+      TS(2);
       PIPE_TICK(32, 15);                         // evaluators waiting for the target
       if (s_ctlB != CTL_RUN) { reached = (s_ctlB == CTL_FINISH); break; }
 
       if (warp == 0) {
         // =========================== COMMIT warp ===========================
         WP_START();
+        if (s_do_commit && s_status == 0) {
+          const PureRes &R = s_res[s_rb];
+          const int cur = s_cur;
+          // node records of the new successors + exact-pose table inserts (hybrid_a_star.py:175-183): lanes 0..nchild-1
+          if (lane < nchild && !s_skip[lane] && s_found[lane] < 0) {
+            const int i = lane, child = s_G + i + 1;
+            if (child >= P.node_cap) s_status = AVP_CAPACITY;
+            else {
+              const int coll = R.coll[i];
+              Node n; n.x = R.cpose[i][0]; n.y = R.cpose[i][1]; n.theta = R.cpose[i][2]; n.parent = cur;
+              n.g = s_g[i]; n.f = 0; n.h = 0;
+              n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); n.in_open = 0;
+              n.in_closed = coll ? 1 : 0; n.hpos = -1;
+              n.in_radius = coll ? 0 : R.inrad[i];
+              nodes[child] = n;
+              if (!coll) nshot[child] = R.shot[i];
+              __threadfence_block();
+              htab_insert(htab, hmask, nodes, child);
+            }
+          }
+          __syncwarp();
+        }
         if (s_do_commit && s_status == 0) {
           const PureRes &R = s_res[s_rb];
           const int cur = s_cur;
@@ -348,9 +519,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
         }
         __syncwarp();
         WP_ACC(1);
-        PIPE_TICK(0, 2);                         // sequential commit
+        TS(3);
+        PIPE_TICK(0, 2);                         // node records + sequential commit
         if (lane == 0 && (s_do_commit || s_status != 0)) do_pop();
         WP_ACC(2);
+        TS(4);
         PIPE_TICK(0, 3);                         // heappop
       } else {
         // =========================== EVALUATORS ===========================
@@ -358,28 +531,30 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
         PureRes &W = s_res[s_rb ^ 1];
         if (!T.valid) { if (etid == 0) W.node = -1; continue; }
         const int phi_np = !T.is_root;             // the root's theta is a Python float (see oracle generate_path)
+        const int nsubs = cfg.n_substeps;
         WP_START();
-        // ---- E0: successor poses, normalised rs queries, sub-step poses (threads of evaluator warps 1..);
-        //          evaluator warp 0: the shot's course plan from the stored word (generate_local_course, rs_curve.py:537-594)
+        // ---- E0: successor poses with their normalised rs queries, and sub-step poses (hybrid_a_star.py:145-151, :185-194),
+        //          spread over the warps (one or two code paths per warp)
         if (etid == 0) {
-          s_shot_coll = 0; s_shot_bad = 0; s_nplan = 0; s_work = 0;
-          for (int i = 0; i < nchild; ++i) s_valid[i] = 0ull;
+          s_nplan = 0; s_work = 0;
+          if (!CLUSTER) { s_shot_coll = 0; s_shot_bad = 0; }       // cluster mode: the helper CTA owns these flags and s_chit
+          for (int i = 0; i < nchild; ++i) { s_valid[i] = 0ull; if (!CLUSTER) s_chit[i] = 0; }
         }
         {
-          const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
-          for (int item = etid - 32; item >= 0 && item < nchild + nchild * nsub; item += ET - 32) {
+          const int nsub = CLUSTER ? 0 : (nsubs <= 4 ? nsubs : 4);
+          for (int item = ewarp + NE * lane; item < nchild + nchild * nsub; item += NE * 32) {
             if (item < nchild) {
               const int c = item;
               double q0[3];
               const double tn = cfg.tan_steer[c % cfg.steering_angle_num];
               const double speed = (c < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
               const double td = speed * cfg.dt;
-              q0[2] = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);            // hybrid_a_star.py:145-151
+              q0[2] = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
               q0[0] = T.x + td * d_cos(q0[2]); q0[1] = T.y + td * d_sin(q0[2]);
               W.cpose[c][0] = q0[0]; W.cpose[c][1] = q0[1]; W.cpose[c][2] = q0[2];
               rs_query(q0, goal, maxc, s_Q[c]);
             } else {
-              const int i = (item - nchild) / nsub, k = (item - nchild) % nsub;
+              const int nsd = nsub > 0 ? nsub : 1, i = (item - nchild) / nsd, k = (item - nchild) % nsd;
               const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
               const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
               const double td_i = speed * cfg.ddt * (k + 1);
@@ -389,117 +564,95 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
             }
           }
         }
-        if (ewarp == 0 && T.in_radius) {
-          if (lane == 0) {
-            RsBest b; b.ok = 0; b.degenerate = 0; b.n = 0; b.ct = 0; b.L = 0.0; b.inst = -1;
-            if (!T.shot.ok) s_shot_bad = 1;
-            else {
-              unsigned mask;
-              b.ok = 1; b.inst = T.shot.inst; b.L = T.shot.L;
-              b.n = rs_arrange(T.shot.inst, T.shot.t, T.shot.u, T.shot.v, 1, phi_np, b.len, b.ct, mask);
-              if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
-            }
-            s_best = b;
-            s_tcs[0] = d_cos(-T.theta); s_tcs[1] = d_sin(-T.theta);
-          }
-          __syncwarp();
-          WP_ACC(4);
-          if (!s_shot_bad) {
-            const int nseg = s_best.n;
-            const char *mode = rs_ct_names[s_best.ct];
-            if (lane < nseg) {
-              double oyaw = 0.0;                                        // heading at the start of segment `lane`
-              for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
-              double ix, iy, yaw_next = oyaw; int dir;
-              rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
-              s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;    // increments for now
-            }
-            __syncwarp();
-            WP_ACC(5);
-            if (lane == 0) {
-              const double step = 0.5 * maxc;
-              s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
-              for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
-              int ind = 1; double d, pd, ll = 0.0;
-              CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
-              for (int i = 0; i < nseg; ++i) {
-                const double l = s_best.len[i];
-                d = (l > 0.0) ? step : -step;
-                ind -= 1;
-                if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
-                while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
-                if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
-                ll = l - pd - d;
-                ind += 1; CYAW[ind] = l; CDIR[ind] = i;
-              }
-              s_nplan = ind + 1;
-            }
-            WP_ACC(6);
-          }
-        }
         WP_ACC(0);
+        TS(3);
         eval_barrier<ET>();
+        TS(4);
         WP_START();
         PIPE_TICK(32, 7);                          // E0
-        if (s_shot_bad) {                          // uniform: the commit warp turns this into the scenario's status
-          if (etid == 0) { W.node = T.node; W.in_radius = T.in_radius; W.shot_bad = s_shot_bad; W.shot_coll = 0; W.shot_ok = 0; }
-          continue;
-        }
-        // ---- E1: rs word instances of the successors (item = inst * nchild + row: a warp runs one word formula on
-        //          different poses) || the shot's course points in the local frame (rs_curve.py:597-624)
+        // ---- E1: one queue of warp items, longest first:
+        //   0                      the shot's course from the node's stored word: plan (generate_local_course, rs_curve.py:537-594)
+        //                          and points in the local frame (:597-624)
+        //   1 .. RS_NITEM          rs word instances (rs_item_inst: up to three instances x all successors per warp item)
+        //   RS_NITEM+1 ..          the successors' sub-step collision checks (hybrid_a_star.py:185-204), one successor each
         {
-          const int n_rs = nchild * RS_NINST, nplan = s_nplan;
-          const char *mode = rs_ct_names[s_best.ct];
-          for (int item = etid; item < n_rs + nplan; item += ET) {
-            if (item < n_rs) {
-              const int inst = item / nchild, row = item - inst * nchild;
-              double t, u, v;
-              if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
-                RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
-                c.L = rs_cand_L(inst, c, 1, 1);
-                s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
-              }
-            } else {
-              const int j = item - n_rs;
-              if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
-              const int seg = CDIR[j]; const double l = CYAW[j];
-              double px, py, pyaw = 0.0; int dir;
-              rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
-              if (mode[seg] == 'S') pyaw = s_org[seg][2];
-              CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
-            }
-          }
-        }
-        WP_ACC(1);
-        eval_barrier<ET>();
-        WP_START();
-        PIPE_TICK(32, 12);                         // E1
-        // ---- E2: set_path de-duplication + minimum per (row, ctype group) on the first SELW warps; every warp then
-        //          takes collision work from a queue: the successors' sub-step checks (hybrid_a_star.py:185-204) first,
-        //          then the shot's course points (:334-347; trailing points with local x == 0.0 dropped, rs_curve.py:588-592)
-        if (ewarp < SELW) {
-          for (int item = etid; item < nchild * RS_NGROUP; item += SELW * 32) {
-            const int g = item / nchild, row = item - g * nchild;
-            rs_select_group(s_cand[row], s_valid[row], g, 1, 1, maxc, s_grp[row][g]);
-          }
-          if (lane == 0) s_wp[warp][7] += clock_ordered() - wt;      // selection part of E2 (also contained in phase 2)
-        }
-        {
-          int npts = 0;
-          if (T.in_radius) {
-            if (lane == 0) { int n = s_nplan; while (n > 0 && CX[n - 1] == 0.0) --n; npts = n; }
-            npts = __shfl_sync(AVP_FULL_MASK, npts, 0);
-          }
-          const int n_items = nchild + npts;
+          const int n_items = CLUSTER ? RS_NITEM : 1 + RS_NITEM + nchild;       // cluster mode: the helper CTA has items 0 and RS_NITEM+1..
           for (;;) {
             int it = 0;
             if (lane == 0) it = atomicAdd(&s_work, 1);
             it = __shfl_sync(AVP_FULL_MASK, it, 0);
             if (it >= n_items) break;
-            if (it < nchild) {
-              const int i = it;
+            if (CLUSTER) it += 1;
+            if (it == 0) {
+              if (!T.in_radius) continue;
+              if (lane == 0) {
+                RsBest b; b.ok = 0; b.degenerate = 0; b.n = 0; b.ct = 0; b.L = 0.0; b.inst = -1;
+                if (!T.shot.ok) s_shot_bad = 1;
+                else {
+                  unsigned mask;
+                  b.ok = 1; b.inst = T.shot.inst; b.L = T.shot.L;
+                  b.n = rs_arrange(T.shot.inst, T.shot.t, T.shot.u, T.shot.v, 1, phi_np, b.len, b.ct, mask);
+                  if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
+                }
+                s_best = b;
+                s_tcs[0] = d_cos(-T.theta); s_tcs[1] = d_sin(-T.theta);
+              }
+              __syncwarp();
+              if (s_shot_bad) continue;
+              const int nseg = s_best.n;
+              const char *mode = rs_ct_names[s_best.ct];
+              if (lane < nseg) {
+                double oyaw = 0.0;                                        // heading at the start of segment `lane`
+                for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
+                double ix, iy, yaw_next = oyaw; int dir;
+                rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
+                s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;    // increments for now
+              }
+              __syncwarp();
+              if (lane == 0) {
+                const double step = 0.5 * maxc;
+                s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
+                for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
+                int ind = 1; double d, pd, ll = 0.0;
+                CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
+                for (int i = 0; i < nseg; ++i) {
+                  const double l = s_best.len[i];
+                  d = (l > 0.0) ? step : -step;
+                  ind -= 1;
+                  if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
+                  while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
+                  if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
+                  ll = l - pd - d;
+                  ind += 1; CYAW[ind] = l; CDIR[ind] = i;
+                }
+                s_nplan = ind + 1;
+              }
+              __syncwarp();
+              if (s_shot_bad) continue;
+              const int nplan = s_nplan;
+              for (int j = lane; j < nplan; j += 32) {
+                if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
+                const int seg = CDIR[j]; const double l = CYAW[j];
+                double px, py, pyaw = 0.0; int dir;
+                rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
+                if (mode[seg] == 'S') pyaw = s_org[seg][2];
+                CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
+              }
+            } else if (it <= RS_NITEM) {
+              const int k = lane / nchild, row = lane - k * nchild;
+              const int inst = (k < 3) ? rs_item_inst[it - 1][k] : -1;
+              if (inst >= 0) {
+                double t, u, v;
+                if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
+                  RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
+                  c.L = rs_cand_L(inst, c, 1, 1);
+                  s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
+                }
+              }
+            } else {
+              const int i = it - 1 - RS_NITEM;
               int coll = 0;
-              for (int k = 0; k < cfg.n_substeps; ++k) {
+              for (int k = 0; k < nsubs; ++k) {
                 bool hit;
                 if (k < 4) hit = check_pose_cs_warp(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3]);
                 else {
@@ -511,7 +664,53 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
                 }
                 if (hit) { coll = 1; break; }
               }
-              if (lane == 0) W.coll[i] = coll;
+              if (lane == 0) s_chit[i] = coll;
+            }
+          }
+        }
+        WP_ACC(1);
+        TS(5);
+        eval_barrier<ET>();
+        TS(6);
+        WP_START();
+        PIPE_TICK(32, 12);                         // E1
+        // ---- E2: a second queue:
+        //   0 .. nchild-1   per successor: set_path de-duplication + minimum per ctype group (lanes = groups), then lane 0:
+        //                   calc_optimal_path (combine the groups), the word kept for the successor's own shot, in_radius, cell id
+        //   nchild ..       collision checks of the shot's course points (hybrid_a_star.py:334-347; trailing points with
+        //                   local x == 0.0 dropped, rs_curve.py:588-592)
+        if (etid == 0) { W.node = T.node; W.in_radius = T.in_radius; W.shot_ok = (T.in_radius && T.shot.ok) ? 1 : 0; }
+        {
+          int npts = 0;
+          if (!CLUSTER && T.in_radius && !s_shot_bad) {
+            if (lane == 0) { int n = s_nplan; while (n > 0 && CX[n - 1] == 0.0) --n; npts = n; }
+            npts = __shfl_sync(AVP_FULL_MASK, npts, 0);
+          }
+          const int n_items = nchild + npts;
+          // s_work was left >= the E1 item count by every warp; the E2 counter continues from a common base
+          const int base = (CLUSTER ? RS_NITEM : 1 + RS_NITEM + nchild) + NE;
+          for (;;) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&s_work, 1) - base;
+            it = __shfl_sync(AVP_FULL_MASK, it, 0);
+            if (it >= n_items) break;
+            if (it < nchild) {
+              const int i = it;
+              if (lane < RS_NGROUP) rs_select_group(s_cand[i], s_valid[i], lane, 1, 1, maxc, s_grp[i][lane]);
+              __syncwarp();
+              if (lane == 0) {
+                RsBest b; rs_combine_groups(s_grp[i], s_cand[i], 1, 1, b);
+                const int ok = (b.ok && !b.degenerate) ? 1 : 0;
+                W.rsok[i] = ok;
+                W.rsL[i] = b.ok ? b.L / maxc : 0.0;
+                NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
+                if (b.ok) { w.t = s_cand[i][b.inst].t; w.u = s_cand[i][b.inst].u; w.v = s_cand[i][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = ok; }
+                W.shot[i] = w;
+                const double x_ = W.cpose[i][0], y_ = W.cpose[i][1];
+                W.inrad[i] = sqrt(d_pow2(x_ - goal[0]) + d_pow2(y_ - goal[1])) < cfg.flag_radius;       // hybrid_a_star.py:308-310
+                const long long id = map_index(S, x_, y_);
+                W.hid[i] = (id >= 0 && id < S.n_ids) ? (int)id : -1;
+              }
             } else {
               const int j = it - nchild;
               const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
@@ -524,36 +723,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
           }
         }
         WP_ACC(2);
-        eval_barrier<ET>();
-        WP_START();
+        TS(7);
         PIPE_TICK(32, 13);                         // E2
-        // ---- E3: calc_optimal_path per successor (combine the groups), the word kept for its own shot, in_radius, cell id
-        if (etid < nchild) {
-          const int i = etid;
-          RsBest b; rs_combine_groups(s_grp[i], s_cand[i], 1, 1, b);
-          const int ok = (b.ok && !b.degenerate) ? 1 : 0;
-          W.rsok[i] = ok;
-          W.rsL[i] = b.ok ? b.L / maxc : 0.0;
-          NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
-          if (b.ok) { w.t = s_cand[i][b.inst].t; w.u = s_cand[i][b.inst].u; w.v = s_cand[i][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = ok; }
-          W.shot[i] = w;
-          const double x_ = W.cpose[i][0], y_ = W.cpose[i][1];
-          W.inrad[i] = sqrt(d_pow2(x_ - goal[0]) + d_pow2(y_ - goal[1])) < cfg.flag_radius;       // hybrid_a_star.py:308-310
-          const long long id = map_index(S, x_, y_);
-          W.hid[i] = (id >= 0 && id < S.n_ids) ? (int)id : -1;
-        } else if (etid == 32) {
-          W.node = T.node; W.in_radius = T.in_radius; W.shot_bad = 0;
-          W.shot_coll = T.in_radius ? *(volatile int *)&s_shot_coll : 0;
-          W.shot_ok = (T.in_radius && T.shot.ok) ? 1 : 0;
-        }
-        WP_ACC(3);
-        PIPE_TICK(32, 14);                         // E3
       }
     }
     __syncthreads();
 
     // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
-    if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 8; for (int k = 0; k < 8; ++k) o[k] = s_wp[warp][k]; }
+    if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] = s_wp[warp][k]; }
     if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] = pc[7]; o[12] = pc[12]; o[13] = pc[13]; o[14] = pc[14]; o[15] = pc[15]; }
     if (tid == 0) {
       avp_plan_summary &R = P.sums[sc];
@@ -606,4 +783,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) {
 #undef PIPE_TICK
 #undef WP_START
 #undef WP_ACC
+#undef TS
+#undef SYNC_AB
+  if (CLUSTER) cluster.sync();        // a CTA's shared memory stays valid until its peer has read the last exit word
 }
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) { search_pipe_body<BLOCK, false>(P); }
+
+template <int BLOCK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BLOCK, 1) k_search_pipe2(KParams P) { search_pipe_body<BLOCK, true>(P); }

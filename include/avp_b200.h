@@ -197,9 +197,10 @@ int avp_set_watchdog(avp_ctx *ctx, long long cycles);
 int avp_fetch_debug(avp_ctx *ctx, int32_t *out8n);
 /* per-scenario SM-cycle accumulators / counters of the search kernel (16 int64 each, see avp_api.cu) */
 int avp_fetch_profile(avp_ctx *ctx, int64_t *out8n);
-/* pipelined pass-2 kernel only: per scenario and warp (16 x 8 int64), the cycles lane 0 of the warp spent
- * WORKING in each evaluator phase (time at the phase barriers excluded) */
-int avp_fetch_warp_profile(avp_ctx *ctx, int64_t *out128n);
+/* pipelined pass-2 kernel only: per scenario and warp (16 x 24 int64): [0..7] the cycles lane 0 of the warp spent
+ * WORKING in each evaluator phase (time at the phase barriers excluded), [8..23] absolute clocks of the warp at
+ * the phase boundaries of the pop selected with the environment variable AVP_TRACE_POP (development aid) */
+int avp_fetch_warp_profile(avp_ctx *ctx, int64_t *out384n);
 
 #ifdef __cplusplus
 }

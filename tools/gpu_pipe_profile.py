@@ -18,8 +18,8 @@ s = res.summaries
 print('search ms', ms, 'passes', dp.last_search_passes(), 'successors', res.successors)
 long_ = np.where(s['n_pops'] >= 20000)[0]
 mid = np.where((s['n_pops'] >= 1024) & (s['n_pops'] < 20000))[0]
-names = {0: 'C init+dij0', 1: 'C accept+lookups+predict', 2: 'C commit', 3: 'C heappop', 4: 'C wait for E',
-         7: 'E0 poses+plan', 12: 'E1 rs+points', 13: 'E2 select+collision', 14: 'E3 combine', 15: 'E wait for C'}
+names = {0: 'C init+dij0', 1: 'C accept+lookups+predict', 2: 'C records+commit', 3: 'C heappop', 4: 'C wait for E',
+         7: 'E0 poses', 12: 'E1 course|rs|substep checks', 13: 'E2 select+combine|course checks', 15: 'E wait for C'}
 for nm, idx in (('long(20000 pops)', long_), ('mid(1024..20000)', mid)):
     if len(idx) == 0:
         continue
@@ -31,12 +31,21 @@ for nm, idx in (('long(20000 pops)', long_), ('mid(1024..20000)', mid)):
     print('   hits/pop %.4f  misses/pop %.4f' % ((p[:, 5] / pops).mean(), (p[:, 6] / pops).mean()))
     print('   push cycles/pop %.0f pushes/pop %.2f | dijkstra cycles/pop %.0f resumes/scenario %.1f' %
           ((p[:, 8] / pops).mean(), (p[:, 9] / pops).mean(), (p[:, 10] / pops).mean(), p[:, 11].mean()))
-    print('   C total/pop %.0f   E total/pop %.0f' % ((p[:, 1:5].sum(1) / pops).mean(), (p[:, [7, 12, 13, 14, 15]].sum(1) / pops).mean()))
+    print('   C total/pop %.0f   E total/pop %.0f' % ((p[:, 1:5].sum(1) / pops).mean(), (p[:, [7, 12, 13, 15]].sum(1) / pops).mean()))
 
 wp = dp.warp_profile()
 if len(long_):
-    w = wp[long_].astype(np.float64) / s['n_pops'][long_].astype(np.float64)[:, None, None]
+    w = wp[long_][:, :, :8].astype(np.float64) / s['n_pops'][long_].astype(np.float64)[:, None, None]
     w = w.mean(0)
-    print('per-warp WORK cycles/pop (long scenarios): E0 E1 E2 E3 | plan:arrange increments planloop | select')
+    print('per-warp WORK cycles/pop (long scenarios; warp 0 = commit warp: lookups, commit, heappop): E0 E1 E2')
     for k in range(16):
-        print('  warp %2d  %7.0f %7.0f %7.0f %7.0f | %7.0f %7.0f %7.0f | %7.0f' % (k, w[k, 0], w[k, 1], w[k, 2], w[k, 3], w[k, 4], w[k, 5], w[k, 6], w[k, 7]))
+        print('  warp %2d  %7.0f %7.0f %7.0f' % (k, w[k, 0], w[k, 1], w[k, 2]))
+
+if os.environ.get('AVP_TRACE_POP') and len(long_):
+    ev = ['afterA', 'arrB', 'afterB', 'arr1|Ccommit', 'aft1|Cpop', 'arr2', 'aft2', 'arrA']
+    for sc_i in long_[:3]:
+        t = wp[sc_i][:, 8:16].astype(np.int64)
+        t0 = t[t > 0].min() if (t > 0).any() else 0
+        print('timeline of pop %s, scenario %d (cycles since the first stamp): %s' % (os.environ['AVP_TRACE_POP'], sc_i, ' '.join(ev)))
+        for k in range(16):
+            print('  warp %2d ' % k + ' '.join('%7d' % (x - t0 if x > 0 else -1) for x in t[k]))
