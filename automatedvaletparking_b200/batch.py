@@ -136,6 +136,15 @@ class DevicePlanner:
                  "avp_collision_check")
         return out.astype(bool)
 
+    def corridor(self, s: int, poses, expand_dis: float):
+        """compute_collision_H distances per path point: (m, 4) = x_max, y_max, x_min, y_min and a status vector
+        (1 = heading outside [-pi, pi], where the reference raises)"""
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        out = np.zeros((p.shape[0], 4))
+        st = np.zeros(p.shape[0], dtype=np.int32)
+        self._ck(self._L.avp_corridor(self._h, s, p.shape[0], _dp(p), float(expand_dis), _dp(out), _ip(st)), "avp_corridor")
+        return out, st
+
     def start_goal_collisions(self):
         """distance_checker.check at every loaded scenario's start and goal pose (scenario recipes)."""
         from . import hostcfg  # noqa: F401

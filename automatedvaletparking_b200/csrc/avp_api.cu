@@ -277,6 +277,25 @@ extern "C" int avp_collision_check(avp_ctx *ctx, int s, int m, const double *pos
   return 0;
 }
 
+extern "C" int avp_corridor(avp_ctx *ctx, int s, int m, const double *poses, double expand_dis, double *out4, int32_t *status) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n || m < 0 || !poses || !out4 || !status) FAIL("avp_corridor: bad arguments");
+  if (!ctx->rasterised) FAIL("avp_corridor: call avp_rasterise first");
+  if (m == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t pb = sizeof(double) * 3 * m, ob = sizeof(double) * 4 * m;
+  if (ensure_scratch(ctx, pb + ob + sizeof(int32_t) * m + 64)) return -1;
+  double *d_p = (double *)ctx->d_scratch, *d_o = d_p + 3 * (size_t)m; int32_t *d_s = (int32_t *)(d_o + 4 * (size_t)m);
+  CK(cudaMemcpyAsync(d_p, poses, pb, cudaMemcpyHostToDevice, ctx->stream));
+  const int wpb = 4, blocks = (m + wpb - 1) / wpb;
+  k_corridor<<<blocks, wpb * 32, 0, ctx->stream>>>(ctx->cfg, ctx->d_scen, s, ctx->d_cells, ctx->d_col, expand_dis, m, d_p, d_o, d_s); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out4, d_o, ob, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(status, d_s, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 extern "C" int avp_expand_pure(avp_ctx *ctx, int s, const double parent_pose[3], double *out_pose, int32_t *out_flags, double *out_rsL) {
   if (!ctx) return -3;
   if (s < 0 || s >= ctx->n) FAIL("avp_expand_pure: scenario index out of range");

@@ -202,6 +202,76 @@ __global__ void __launch_bounds__(128) k_check_batch(avp_config cfg, const ScenD
   if ((threadIdx.x & 31) == 0) out[w] = hit ? 1 : 0;
 }
 
+// Corridor extraction: path_opti.compute_collision_H (optimization/path_optimazition.py:221-658)
+// and its copy ocp_optimization.compute_collision_H (optimization/ocp_optimization.py:36-480).
+// One warp per path point; the lanes scan the obstacle cells of the raster columns covered by the AABB of the
+// inflated vehicle rectangle + expand_dis (the cell list is sorted by column, np.where order), classify each
+// cell into the first of the four areas (right, front, left, rear) whose heading-dependent box contains it
+// (:375-645) and keep per lane the minima of the horizontal / vertical distances to that edge; the four minima
+// are order independent, so the warp reduction reproduces the reference's sequential loop exactly.
+// out4[w] = {x_max, y_max, x_min, y_min} (each <= expand_dis), status[w] = 1 for a heading outside [-pi, pi]
+// (the reference leaves `case` unbound there).
+__global__ void __launch_bounds__(128) k_corridor(avp_config cfg, const ScenDev *scen, int s, const double2 *cells_all, const int32_t *col_all,
+                                                  double expand_dis, int m, const double *poses, double *out4, int32_t *status) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= m) return;
+  const ScenDev &S = scen[s];
+  const double2 *cells = cells_all + S.cell_off;
+  const int32_t *col_start = col_all + S.col_off;
+  const double x = poses[3 * w], y = poses[3 * w + 1], th = poses[3 * w + 2], e = expand_dis;
+  int shift;
+  if (th >= -AVP_PI && th < -AVP_PI / 2) shift = 2;          // case 3
+  else if (th >= -AVP_PI / 2 && th < 0) shift = 3;           // case 4
+  else if (th >= 0 && th < AVP_PI / 2) shift = 0;            // case 1
+  else if (th >= AVP_PI / 2 && th <= AVP_PI) shift = 1;      // case 2
+  else { if (lane < 4) out4[4 * w + lane] = NAN; if (lane == 0) status[w] = 1; return; }
+  const double sn = d_sin(th), cs = d_cos(th);
+  VehGeom g;
+  veh_geom(cfg, x, y, cs, sn, g);                            // corners, k, b, sqrt(1 + k*k) of the four edges
+  const double bx_max = g.x_max + e, bx_min = g.x_min - e, by_max = g.y_max + e, by_min = g.y_min - e;   // :255-258
+  double a0[4], a1[4], a2[4], a3[4];                         // get_area_boundary (:289-294) with the box of (case, area) applied
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double p1x = g.vb[k][0], p1y = g.vb[k][1], p2x = g.vb[k + 1][0], p2y = g.vb[k + 1][1];     // vb[4] == vb[0]
+    const int q = (k + shift) & 3;
+    const int sx = (q < 2) ? 1 : -1, sy = (q == 1 || q == 2) ? 1 : -1;
+    const double xl = (p2x < p1x) ? p2x : p1x, xh = (p2x > p1x) ? p2x : p1x, yl = (p2y < p1y) ? p2y : p1y, yh = (p2y > p1y) ? p2y : p1y;
+    a0[k] = (sx < 0) ? xl - e : xl; a1[k] = (sx > 0) ? xh + e : xh;
+    a2[k] = (sy < 0) ? yl - e : yl; a3[k] = (sy > 0) ? yh + e : yh;
+  }
+  const double as = fabs(sn), ac = fabs(cs);
+  double x_max = e, x_min = e, y_max = e, y_min = e;
+  int lo, hi;
+  col_range(S, bx_min, bx_max, lo, hi);
+  if (lo <= hi) {
+    const int beg = col_start[lo], end = col_start[hi + 1];
+    for (int i = beg + lane; i < end; i += 32) {
+      const double2 p = cells[i];
+      if (!(p.x >= bx_min && p.x <= bx_max && p.y >= by_min && p.y <= by_max)) continue;          // :266-275
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (p.x > a0[k] && p.x < a1[k] && p.y > a2[k] && p.y < a3[k]) {
+          const double sd = fabs(g.lk[k] * p.x + g.lb[k] - p.y) / g.ls[k];                         // compute_distance (:296-298)
+          const double ver = sd / ac, hor = sd / as;                                                   // :303-305
+          const int q = (k + shift) & 3;
+          if (q < 2) { if (hor < x_max) x_max = hor; } else { if (hor < x_min) x_min = hor; }
+          if (q == 1 || q == 2) { if (ver < y_max) y_max = ver; } else { if (ver < y_min) y_min = ver; }
+          break;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double v;
+    v = shfl_dbl(x_max, lane ^ o); if (v < x_max) x_max = v;
+    v = shfl_dbl(y_max, lane ^ o); if (v < y_max) y_max = v;
+    v = shfl_dbl(x_min, lane ^ o); if (v < x_min) x_min = v;
+    v = shfl_dbl(y_min, lane ^ o); if (v < y_min) y_min = v;
+  }
+  if (lane == 0) { out4[4 * w] = x_max; out4[4 * w + 1] = y_max; out4[4 * w + 2] = x_min; out4[4 * w + 3] = y_min; status[w] = 0; }
+}
+
 // rs length (normalised-by-maxc L/maxc) of pose -> goal, warp-collective; cand: 46 entries of shared memory
 __device__ __forceinline__ void rs_length_warp(const double q0[3], const double q1[3], double maxc, int xy_np, int phi_np,
                                                RsCand *cand, RsBest &best) {
@@ -644,13 +714,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       if (lane == 0) {
         if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
         s_nhq++;
-        if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
+        if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;     // the reference never returns from this compute_path: no root node
+        else {
         Node r; r.x = S.pose[0]; r.y = S.pose[1]; r.theta = pi_2_pi(S.pose[2]); r.f = 0; r.g = 0; r.h = 0; r.parent = -1;
         r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0;
         r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
         { int n_ = s_on; oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
+        }
       }
     }
 

@@ -318,13 +318,15 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
       if (lane == 0) {
         if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
         s_nhq++;
-        if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
+        if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;     // the reference never returns from this compute_path: no root node
+        else {
         Node r; r.x = S.pose[0]; r.y = S.pose[1]; r.theta = pi_2_pi(S.pose[2]); r.f = 0; r.g = 0; r.h = 0; r.parent = -1;
         r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0;
         r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
         { int n_ = s_on; oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
+        }
       }
     } else if (warp == 1) {
       const double q0[3] = {S.pose[0], S.pose[1], pi_2_pi(S.pose[2])};

@@ -125,6 +125,13 @@ int avp_fetch_map(avp_ctx *ctx, int s, int32_t *dims, double *geom, uint8_t *cos
  * for m poses (x,y,theta triples) against scenario s's raster; out[m] = 0/1. */
 int avp_collision_check(avp_ctx *ctx, int s, int m, const double *poses, uint8_t *out);
 
+/* replaces the obstacle-raster scan of path_opti.compute_collision_H (optimization/path_optimazition.py:221-658)
+ * and ocp_optimization.compute_collision_H (optimization/ocp_optimization.py:36-480) for m path points
+ * (x,y,theta triples, theta in [-pi, pi]) of scenario s: out4[4*i..] = x_max, y_max, x_min, y_min, the free
+ * distances (<= expand_dis) the reference turns into H_max = (x_max + x, y_max + y), H_min = (x - x_min, y - y_min)
+ * (:651-654).  status[i] = 1 (and NaNs) for a heading outside [-pi, pi]: the reference raises UnboundLocalError. */
+int avp_corridor(avp_ctx *ctx, int s, int m, const double *poses, double expand_dis, double *out4, int32_t *status);
+
 /* replaces hybrid_a_star.expand_node's pure part for one parent (hybrid_a_star.py:133-151,
  * 185-204) + rs length (calc_node_heuristic's h_value_2): for each of the 2*n primitives
  * out_pose[3] and out_flags (bit0 = collision on a sub-step, bit1 = outside boundary),

@@ -316,6 +316,70 @@ int orc_check(const orc_map *m, const avp_config *cfg, double x, double y, doubl
   return cfg->collision_mode == 1 ? check_circle(m, cfg, x, y, th) : check_distance(m, cfg, x, y, th);
 }
 
+/* ------------------------------------------------------------------ corridor extraction */
+
+/* path_opti.compute_collision_H (optimization/path_optimazition.py:221-658) and its copy
+ * ocp_optimization.compute_collision_H (optimization/ocp_optimization.py:36-480), per path point:
+ * the free distances x_max, y_max, x_min, y_min (each <= expand_dis) from the inflated vehicle rectangle
+ * to the obstacle raster cells around it.  out4[i] = {x_max, y_max, x_min, y_min}; the reference then forms
+ * H_max = (x_max + x, y_max + y), H_min = (x - x_min, y - y_min) (:651-654).  A heading outside [-pi, pi]
+ * leaves `case` unbound in the reference (UnboundLocalError): status[i] = 1 and NaNs.
+ * Quirks kept: vehicle_boundary has shape (5,2,1), so k, b are 1-element arrays and pow(_k, 2) is
+ * numpy's array power (a multiplication, not libm pow); the areas are tested in the order right, front,
+ * left, rear and the first hit wins (break); inf/nan slopes of axis-aligned headings flow through IEEE
+ * comparisons; a quotient by |sin|,|cos| = 0 gives inf/nan and never updates a minimum. */
+void orc_corridor(const orc_map *m, const avp_config *cfg, double expand_dis, int n, const double *poses, double *out4, int32_t *status) {
+  static const int base_x[4] = {+1, +1, -1, -1}, base_y[4] = {-1, +1, +1, -1};   /* case 1: right, front, left, rear */
+  const double e = expand_dis;
+  for (int p = 0; p < n; ++p) {
+    const double x = poses[3 * p], y = poses[3 * p + 1], th = poses[3 * p + 2];
+    double *o = out4 + 4 * p;
+    int shift;
+    if (th >= -PI && th < -PI / 2) shift = 2;            /* case 3 */
+    else if (th >= -PI / 2 && th < 0) shift = 3;         /* case 4 */
+    else if (th >= 0 && th < PI / 2) shift = 0;          /* case 1 */
+    else if (th >= PI / 2 && th <= PI) shift = 1;        /* case 2 */
+    else { o[0] = o[1] = o[2] = o[3] = NAN; if (status) status[p] = 1; continue; }
+    if (status) status[p] = 0;
+    double vb[5][2];
+    vehicle_corners(cfg, x, y, th, vb);
+    double bx_max = vb[0][0], bx_min = vb[0][0], by_max = vb[0][1], by_min = vb[0][1];
+    for (int i = 1; i < 5; ++i) {
+      if (vb[i][0] > bx_max) bx_max = vb[i][0]; if (vb[i][0] < bx_min) bx_min = vb[i][0];
+      if (vb[i][1] > by_max) by_max = vb[i][1]; if (vb[i][1] < by_min) by_min = vb[i][1];
+    }
+    bx_max += e; bx_min -= e; by_max += e; by_min -= e;                          /* :255-258 */
+    double lk[4], lb_[4], area[4][4];
+    for (int i = 0; i < 4; ++i) {
+      const double *p1 = vb[i], *p2 = vb[(i < 3) ? i + 1 : 0];
+      lk[i] = (p2[1] - p1[1]) / (p2[0] - p1[0]);                                  /* compute_k_b :282-287 */
+      lb_[i] = p1[1] - lk[i] * p1[0];
+      area[i][0] = (p2[0] < p1[0]) ? p2[0] : p1[0]; area[i][1] = (p2[0] > p1[0]) ? p2[0] : p1[0];   /* get_area_boundary :289-294 (python min/max) */
+      area[i][2] = (p2[1] < p1[1]) ? p2[1] : p1[1]; area[i][3] = (p2[1] > p1[1]) ? p2[1] : p1[1];
+    }
+    const double as = fabs(sin(th)), ac = fabs(cos(th));
+    double x_max = e, x_min = e, y_max = e, y_min = e;
+    for (int c = 0; c < m->n_obs; ++c) {
+      const double ox = m->obs_x[c], oy = m->obs_y[c];
+      if (!(ox >= bx_min && ox <= bx_max)) continue;                              /* :266-269 */
+      if (!(oy >= by_min && oy <= by_max)) continue;                              /* :272-275 */
+      for (int k = 0; k < 4; ++k) {
+        const int sx = base_x[(k + shift) & 3], sy = base_y[(k + shift) & 3];
+        const double ax0 = (sx < 0) ? area[k][0] - e : area[k][0], ax1 = (sx > 0) ? area[k][1] + e : area[k][1];
+        const double ay0 = (sy < 0) ? area[k][2] - e : area[k][2], ay1 = (sy > 0) ? area[k][3] + e : area[k][3];
+        if (ox > ax0 && ox < ax1 && oy > ay0 && oy < ay1) {
+          const double sd = fabs(lk[k] * ox + lb_[k] - oy) / sqrt(1 + lk[k] * lk[k]);     /* compute_distance :296-298 */
+          const double ver = sd / ac, hor = sd / as;                                      /* :303-305 */
+          if (sx > 0) { if (hor < x_max) x_max = hor; } else { if (hor < x_min) x_min = hor; }
+          if (sy > 0) { if (ver < y_max) y_max = ver; } else { if (ver < y_min) y_min = ver; }
+          break;
+        }
+      }
+    }
+    o[0] = x_max; o[1] = y_max; o[2] = x_min; o[3] = y_min;
+  }
+}
+
 /* ------------------------------------------------------------------ Reeds-Shepp (path_plan/rs_curve.py) */
 
 typedef struct { int n; double len[5]; char ct[6]; double L; } rs_word;

@@ -80,6 +80,7 @@ def lib():
         L.orc_dij_hvalues.argtypes = [ctypes.c_void_p, c_ip]
         L.orc_plan.restype = ctypes.c_int
         L.orc_plan.argtypes = [ctypes.c_void_p, ctypes.POINTER(AvpConfig), ctypes.POINTER(PlanOut)]
+        L.orc_corridor.argtypes = [ctypes.c_void_p, ctypes.POINTER(AvpConfig), ctypes.c_double, ctypes.c_int, c_dp, c_dp, c_ip]
         L.orc_expand_pure.argtypes = [ctypes.c_void_p, ctypes.POINTER(AvpConfig), c_dp, c_dp, c_ip, c_dp]
         _lib = L
     return _lib
@@ -139,6 +140,14 @@ class OracleMap:
 
     def check(self, cfg, x, y, theta):
         return bool(lib().orc_check(self._h, ctypes.byref(cfg), float(x), float(y), float(theta)))
+
+    def corridor(self, cfg, poses, expand_dis):
+        """compute_collision_H distances (x_max, y_max, x_min, y_min) per pose + status (1: heading outside [-pi, pi])"""
+        p = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+        out = np.zeros((p.shape[0], 4))
+        st = np.zeros(p.shape[0], dtype=np.int32)
+        lib().orc_corridor(self._h, ctypes.byref(cfg), float(expand_dis), p.shape[0], _dp(p), _dp(out), _ip(st))
+        return out, st
 
     def expand_pure(self, cfg, parent):
         n = 2 * cfg.steering_angle_num

@@ -279,3 +279,62 @@ def test_edge_inputs(device_planner, cfg):
         r = small.plan(cap_path=256, cap_pops=16)
         ref = O.plan(O.OracleMap(scn.benchmark_case(1)), small.cfg)
         assert int(r.summaries["status"][0]) == ref["status"] == 5 and np.array_equal(r.pop_indices(0), ref["pops"])
+
+
+def _oracle_many(scs, cfg, threads=None):
+    """the oracle on a thread pool (ctypes releases the GIL); one summary dict per scenario"""
+    from concurrent.futures import ThreadPoolExecutor
+    O.lib()
+
+    def one(sc):
+        r = O.plan(O.OracleMap(sc), cfg, cap_pops=1, cap_path=512)
+        return {k: r[k] for k in ("status", "n_pops", "global_index", "n_closed", "n_open", "n_astar", "n_rs", "n_final", "n_hq", "h_closed", "n_hcalls",
+                                  "final_path", "rs_L", "rs_ctypes")}
+
+    with ThreadPoolExecutor(max_workers=threads or (os.cpu_count() or 4)) as ex:
+        return list(ex.map(one, scs))
+
+
+def _compare_many(res, scs, refs):
+    s = res.summaries
+    for k, (sc, r) in enumerate(zip(scs, refs)):
+        for key in ("status", "n_pops", "global_index", "n_closed", "n_open", "n_astar", "n_rs", "n_final", "n_hq", "h_closed", "n_hcalls"):
+            assert int(s[key][k]) == r[key], (sc.name, key, int(s[key][k]), r[key])
+        if r["status"] in (0, 2):
+            assert np.array_equal(res.path(k), r["final_path"]), sc.name
+            assert s["rs_ctypes"][k].decode() == r["rs_ctypes"] and s["rs_L"][k] == r["rs_L"], sc.name
+
+
+def test_config2_full_batch_every_scenario_vs_oracle(device_planner, cfg):
+    """BASELINE configs[1] at FULL size: all 1024 scenarios of the bench workload, every summary field and every
+    returned path bit-identical to the oracle (the 51 searches that hit the 20 000-pop cap included)."""
+    import bench
+    dp = device_planner
+    scs = bench.make_scenarios(0, 1024, dp)
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=0)
+    refs = _oracle_many(scs, cfg)
+    _compare_many(res, scs, refs)
+    assert sum(r["status"] == 0 for r in refs) > 900 and sum(r["status"] == 5 for r in refs) > 10
+
+
+def test_config3_all_cases_perturbed_vs_oracle(device_planner, cfg):
+    """BASELINE configs[2] recipe: every BenchmarkCase x 16 perturbed start/goal poses (seed 100 + case), unfiltered
+    (colliding starts are status parity), all against the oracle."""
+    dp = device_planner
+    scs = []
+    for c in range(1, 21):
+        scs += scn.perturbed_set(scn.benchmark_case(c), 16, seed=100 + c)
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=0)
+    _compare_many(res, scs, _oracle_many(scs, cfg))
+
+
+def test_config4_synthetic_batch_vs_oracle(device_planner, cfg):
+    """BASELINE configs[3] recipe: 16 synthetic 200x200 maps (256 polygons each) x 32 start/goal pairs."""
+    dp = device_planner
+    scs = scn.synthetic_set(16, 32, seed=4)
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=0)
+    assert (res.summaries["nx"] == 200).all() and (res.summaries["n_obs"] > 1000).all()
+    _compare_many(res, scs, _oracle_many(scs, cfg))
