@@ -38,7 +38,7 @@ struct avp_ctx {
   // per-slot workspaces
   int ws_slots = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
   NodeShot *d_nshot = nullptr; int nshot_slots = 0, nshot_node_cap = 0;   // pipelined pass-2 kernel only
-  Node *d_nodes = nullptr; int32_t *d_oheap = nullptr, *d_htab = nullptr; unsigned long long *d_dheap = nullptr; double *d_oheap_f = nullptr;
+  Node *d_nodes = nullptr; OEnt *d_oheap = nullptr; int32_t *d_htab = nullptr; unsigned long long *d_dheap = nullptr;
   int slots_wide = 0; int slots_w[3] = {0, 0, 0}; int32_t *d_worklist = nullptr; int worklist_cap = 0;
   int32_t *d_order = nullptr;      // pass-1 processing order: expensive scenarios (far start-goal pairs) first
   double *d_course = nullptr; int32_t *d_course_dir = nullptr;
@@ -129,8 +129,8 @@ static void free_results(avp_ctx *ctx) {
 }
 static void free_ws(avp_ctx *ctx) {
   free_dev(ctx->d_nshot); ctx->d_nshot = nullptr; ctx->nshot_slots = 0; ctx->nshot_node_cap = 0;
-  free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir); free_dev(ctx->d_oheap_f);
-  ctx->d_oheap_f = nullptr; ctx->d_nodes = nullptr; ctx->d_oheap = ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
+  free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir);
+  ctx->d_nodes = nullptr; ctx->d_oheap = nullptr; ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
 }
 
 extern "C" int avp_destroy(avp_ctx *ctx) {
@@ -357,8 +357,7 @@ static int ensure_ws(avp_ctx *ctx) {
   ctx->node_cap = node_cap; ctx->htab_size = hb; ctx->dheap_cap = 1 << 16;
   const int S = slots;        // as many slots as CTAs that can be resident for this batch
   CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)S * node_cap));
-  CK(cudaMalloc(&ctx->d_oheap, sizeof(int32_t) * (size_t)S * node_cap));
-  CK(cudaMalloc(&ctx->d_oheap_f, sizeof(double) * (size_t)S * node_cap));
+  CK(cudaMalloc(&ctx->d_oheap, sizeof(OEnt) * (size_t)S * node_cap));
   CK(cudaMalloc(&ctx->d_htab, sizeof(int32_t) * (size_t)S * hb));
   CK(cudaMalloc(&ctx->d_dheap, sizeof(unsigned long long) * (size_t)S * ctx->dheap_cap));
   CK(cudaMalloc(&ctx->d_course, sizeof(double) * (size_t)S * 3 * AVP_COURSE_CAP));
@@ -425,7 +424,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.cfg = ctx->cfg; if (P.cfg.max_pops <= 0) P.cfg.max_pops = 20000;
   P.n_scen = ctx->n; P.scen = ctx->d_scen; P.cost = ctx->d_cost; P.cells = ctx->d_cells; P.col_start = ctx->d_col;
   P.hval = ctx->d_hval; P.ost = ctx->d_ost; P.gx = ctx->d_gx; P.gy = ctx->d_gy;
-  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.oheap_f = ctx->d_oheap_f;
+  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
   P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof; { const char *tpp = getenv("AVP_TRACE_POP"); P.trace_pop = tpp ? atoi(tpp) : -1; } P.watchdog_cycles = ctx->watchdog_cycles;

@@ -57,8 +57,7 @@ struct KParams {
   unsigned long long *dheap; int dheap_cap;
   Node *nodes; int node_cap;
   NodeShot *nshot;                // node_cap per slot (pipelined kernel only)
-  double *oheap_f;                // open heap keys beyond the shared-memory part (node_cap per slot)
-  int32_t *oheap;                 // open heap node indices beyond the shared-memory part
+  struct OEnt *oheap;             // open heap entries beyond the shared-memory part (node_cap per slot)
   int32_t *htab; int htab_size;   // power of two
   double *course;                 // 3*AVP_COURSE_CAP doubles per slot
   int32_t *course_dir;
@@ -573,42 +572,50 @@ __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node 
 
 // open_list: CPython heapq of Node objects ordered by Node.__lt__ (f only, hybrid_a_star.py:61-68).
 // Entries carry a copy of f (kept in sync on the reference's in-place updates through Node.hpos);
-// the first AVP_SM_OPEN entries live in shared memory.  The functions are force-inlined and take
-// the __shared__ arrays themselves so that the compiler keeps the shared address space.
-#define OH_F(i) ((i) < SMO ? sf[(i)] : gf[(i) - SMO])
-#define OH_I(i) ((i) < SMO ? si[(i)] : gi[(i) - SMO])
-#define OH_SET(i, f_, idx_) do { if ((i) < SMO) { sf[(i)] = (f_); si[(i)] = (idx_); } else { gf[(i) - SMO] = (f_); gi[(i) - SMO] = (idx_); } nodes[(idx_)].hpos = (i); } while (0)
+// the first SMO entries live in shared memory (separate key / index arrays), the rest in global memory as
+// 16-byte records read with ONE load per entry: a level of a sift costs one memory round trip, not two.
+// The functions are force-inlined and take the __shared__ arrays themselves so that the compiler keeps the
+// shared address space.
+struct __align__(16) OEnt { double f; int32_t idx; int32_t pad; };
 template <int SMO>
-__device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int pos, double fi, int item) {   // heapq._siftdown(heap, 0, pos)
+__device__ __forceinline__ void oh_get(const double *sf, const int32_t *si, const OEnt *ge, int i, double &f, int &idx) {
+  if (i < SMO) { f = sf[i]; idx = si[i]; }
+  else { const int4 v = *reinterpret_cast<const int4 *>(&ge[i - SMO]); f = __hiloint2double(v.y, v.x); idx = v.z; }
+}
+#define OH_SET(i, f_, idx_) do { if ((i) < SMO) { sf[(i)] = (f_); si[(i)] = (idx_); } else { int4 v_; v_.x = __double2loint(f_); v_.y = __double2hiint(f_); v_.z = (idx_); v_.w = 0; *reinterpret_cast<int4 *>(&ge[(i) - SMO]) = v_; } nodes[(idx_)].hpos = (i); } while (0)
+template <int SMO>
+__device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, OEnt *ge, Node *nodes, int pos, double fi, int item) {   // heapq._siftdown(heap, 0, pos)
   while (pos > 0) {
-    const int parent = (pos - 1) >> 1; const double pf = OH_F(parent);
-    if (fi < pf) { const int pi = OH_I(parent); OH_SET(pos, pf, pi); pos = parent; continue; }
+    const int parent = (pos - 1) >> 1; double pf; int pi; oh_get<SMO>(sf, si, ge, parent, pf, pi);
+    if (fi < pf) { OH_SET(pos, pf, pi); pos = parent; continue; }
     break;
   }
   OH_SET(pos, fi, item);
 }
 template <int SMO>
-__device__ __forceinline__ void oh_push(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int &n, double f, int idx) {
+__device__ __forceinline__ void oh_push(double *sf, int32_t *si, OEnt *ge, Node *nodes, int &n, double f, int idx) {
   const int pos = n++;
-  oh_siftdown<SMO>(sf, si, gf, gi, nodes, pos, f, idx);
+  oh_siftdown<SMO>(sf, si, ge, nodes, pos, f, idx);
 }
 // heapq.heappop after the root has been read: move the last entry to the root and _siftup
 template <int SMO>
-__device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, double *gf, int32_t *gi, Node *nodes, int &n) {
+__device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, OEnt *ge, Node *nodes, int &n) {
   const int last = n - 1;
-  const double fi = OH_F(last); const int item = OH_I(last);
+  double fi; int item; oh_get<SMO>(sf, si, ge, last, fi, item);
   n = last;
   if (last == 0) return;
   int pos = 0, child = 1;
   while (child < last) {
     const int right = child + 1;
-    double cf = OH_F(child);
-    if (right < last) { const double rf = OH_F(right); if (!(cf < rf)) { child = right; cf = rf; } }
-    const int ci = OH_I(child);
+    double cf; int ci; oh_get<SMO>(sf, si, ge, child, cf, ci);
+    if (right < last) { double rf; int ri; oh_get<SMO>(sf, si, ge, right, rf, ri); if (!(cf < rf)) { child = right; cf = rf; ci = ri; } }
     OH_SET(pos, cf, ci); pos = child; child = 2 * pos + 1;
   }
-  oh_siftdown<SMO>(sf, si, gf, gi, nodes, pos, fi, item);
+  oh_siftdown<SMO>(sf, si, ge, nodes, pos, fi, item);
 }
+// in-place key update of an entry (hybrid_a_star.py:224-230: no re-heapify)
+template <int SMO>
+__device__ __forceinline__ void oh_set_key(double *sf, OEnt *ge, int hpos, double f) { if (hpos < SMO) sf[hpos] = f; else ge[hpos - SMO].f = f; }
 
 // hybrid_a_star.py:243-259
 __device__ __forceinline__ double node_cost(const avp_config &c, bool gear, double theta, double father_theta, bool father_gear) {
@@ -668,8 +675,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
   int32_t *htab = P.htab + (size_t)slot * P.htab_size;
-  double *ogf = P.oheap_f + (size_t)slot * P.node_cap;
-  int32_t *ogi = P.oheap + (size_t)slot * P.node_cap;
+  OEnt *oge = P.oheap + (size_t)slot * P.node_cap;
   const int hmask = P.htab_size - 1;
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
   int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
@@ -721,7 +727,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
         r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
-        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
+        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, oge, nodes, n_, 0.0, 0); s_on = n_; }
         }
       }
     }
@@ -787,7 +793,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
       // Thread 0 takes no item when the CTA is wide enough: it finishes heapq.heappop meanwhile (move the
       // last entry to the root, sift) -- nothing in phases 1-4 touches the open heap.
       constexpr int RS_T0 = (BLOCK >= 512) ? 1 : 0;
-      if (tid == 0) { const long long t_ = clock64(); int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_; pc[13] += clock64() - t_; pc[14] += n_; }
+      if (tid == 0) { const long long t_ = clock64(); int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_; pc[13] += clock64() - t_; pc[14] += n_; }
       for (int item = tid - RS_T0; item >= 0 && item < (nchild + 1) * RS_NINST; item += BLOCK - RS_T0) {
         const int inst = item / (nchild + 1), row = item - inst * (nchild + 1);
         if (row == nchild && !s_in_radius) continue;
@@ -995,13 +1001,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
                 Node &n = nodes[child];
                 const double f = s_g[i] + h;
                 n.h = h; n.f = f; n.in_open = 1;
-                { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; pc[12] += nodes[child].hpos; }
+                { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; pc[12] += nodes[child].hpos; }
               } else {                                                    // :219-230 (in place, no re-heapify)
                 const double new_f = h + s_g[i];
                 if (new_f < s_oldf[i]) {
                   Node &n = nodes[found];
                   n.f = new_f; n.g = s_g[i]; n.h = h; n.parent = cur; n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num);
-                  if (n.hpos < SMO) s_of[n.hpos] = new_f; else ogf[n.hpos - SMO] = new_f;
+                  oh_set_key<SMO>(s_of, oge, n.hpos, new_f);
                 }
               }
             }

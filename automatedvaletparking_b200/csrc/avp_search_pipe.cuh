@@ -105,8 +105,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
   NodeShot *nshot = P.nshot + (size_t)slot * P.node_cap;
   int32_t *htab = P.htab + (size_t)slot * P.htab_size;
-  double *ogf = P.oheap_f + (size_t)slot * P.node_cap;
-  int32_t *ogi = P.oheap + (size_t)slot * P.node_cap;
+  OEnt *oge = P.oheap + (size_t)slot * P.node_cap;
   const int hmask = P.htab_size - 1;
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
   int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
@@ -287,7 +286,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         s_cur = ret;
         if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
         s_npops++;
-        int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, ogf, ogi, nodes, n_); s_on = n_;
+        int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_;
         s_ctlA = CTL_RUN;
       }
     };
@@ -325,7 +324,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
-        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, n_, 0.0, 0); s_on = n_; }
+        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, oge, nodes, n_, 0.0, 0); s_on = n_; }
         }
       }
     } else if (warp == 1) {
@@ -488,13 +487,13 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
                   Node &n = nodes[child];
                   const double f = s_g[i] + h;
                   n.h = h; n.f = f; n.in_open = 1;
-                  { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, ogf, ogi, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; }
+                  { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; }
                 } else {                                                    // :219-230 (in place, no re-heapify)
                   const double new_f = h + s_g[i];
                   if (new_f < s_oldf[i]) {
                     Node &n = nodes[found];
                     n.f = new_f; n.g = s_g[i]; n.h = h; n.parent = cur; n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num);
-                    if (n.hpos < SMO) s_of[n.hpos] = new_f; else ogf[n.hpos - SMO] = new_f;
+                    oh_set_key<SMO>(s_of, oge, n.hpos, new_f);
                   }
                 }
               }
