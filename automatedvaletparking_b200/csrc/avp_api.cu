@@ -425,12 +425,17 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.n_scen = ctx->n; P.scen = ctx->d_scen; P.cost = ctx->d_cost; P.cells = ctx->d_cells; P.col_start = ctx->d_col;
   P.hval = ctx->d_hval; P.ost = ctx->d_ost; P.gx = ctx->d_gx; P.gy = ctx->d_gy;
   P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap;
-  P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
+  P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.htab_stride = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
   P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof; { const char *tpp = getenv("AVP_TRACE_POP"); P.trace_pop = tpp ? atoi(tpp) : -1; } P.watchdog_cycles = ctx->watchdog_cycles;
   const char *pb = getenv("AVP_POP_BUDGET");
   const int budget = pb ? atoi(pb) : 1024;
   P.work_list = ctx->d_order; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
+  {   // pass 1 creates at most nchild * (pop_budget + 1) nodes per scenario: a table of that size is cleared and probed, not the full one
+    const long long need = 2ll * (2 * P.cfg.steering_angle_num) * ((long long)P.pop_budget + 2);
+    int hb = 1024; while (hb < need && hb < ctx->htab_size) hb <<= 1;
+    if (hb < ctx->htab_size) P.htab_size = hb;
+  }
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -452,7 +457,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       if ((int)list.size() > ctx->worklist_cap) { free_dev(ctx->d_worklist); ctx->d_worklist = nullptr; CK(cudaMalloc(&ctx->d_worklist, sizeof(int32_t) * list.size())); ctx->worklist_cap = (int)list.size(); }
       CK(cudaMemcpyAsync(ctx->d_worklist, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-      P.work_list = ctx->d_worklist; P.n_work = (int)list.size(); P.pop_budget = P.cfg.max_pops;
+      P.work_list = ctx->d_worklist; P.n_work = (int)list.size(); P.pop_budget = P.cfg.max_pops; P.htab_size = ctx->htab_size;
       // widest CTA whose persistent grid still holds every pending scenario at once (one wave)
       const int npend = (int)list.size();
       int which = 3;

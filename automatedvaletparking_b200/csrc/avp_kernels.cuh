@@ -58,7 +58,8 @@ struct KParams {
   Node *nodes; int node_cap;
   NodeShot *nshot;                // node_cap per slot (pipelined kernel only)
   struct OEnt *oheap;             // open heap entries beyond the shared-memory part (node_cap per slot)
-  int32_t *htab; int htab_size;   // power of two
+  int32_t *htab; int htab_size;   // power of two: entries used by this launch (pass 1 needs far fewer nodes than max_pops allows)
+  int htab_stride;                // entries between two slots' tables
   double *course;                 // 3*AVP_COURSE_CAP doubles per slot
   int32_t *course_dir;
   // results per scenario
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 
   const int nchild = 2 * cfg.steering_angle_num;
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
-  int32_t *htab = P.htab + (size_t)slot * P.htab_size;
+  int32_t *htab = P.htab + (size_t)slot * P.htab_stride;
   OEnt *oge = P.oheap + (size_t)slot * P.node_cap;
   const int hmask = P.htab_size - 1;
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;

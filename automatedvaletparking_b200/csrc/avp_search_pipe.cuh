@@ -104,7 +104,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
   NodeShot *nshot = P.nshot + (size_t)slot * P.node_cap;
-  int32_t *htab = P.htab + (size_t)slot * P.htab_size;
+  int32_t *htab = P.htab + (size_t)slot * P.htab_stride;
   OEnt *oge = P.oheap + (size_t)slot * P.node_cap;
   const int hmask = P.htab_size - 1;
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
