@@ -108,7 +108,6 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   cudaFuncSetAttribute(k_search_pipe<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
   cudaFuncSetAttribute(k_search_pipe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
   cudaFuncSetAttribute(k_search_pipe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(128));
-  cudaFuncSetAttribute(k_search_pipe2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
   *out = ctx;
@@ -478,15 +477,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       }
       P.nshot = ctx->d_nshot;
       CK(cudaEventRecord(ctx->ev0, ctx->stream));
-      // AVP_CLUSTER=1: two-CTA thread-block clusters (one scenario on two SMs, collision work on the second CTA)
-      const char *ce = getenv("AVP_CLUSTER");
-      const bool use_cluster = pipe && which == 0 && (ce && atoi(ce) == 1) && ctx->n_sm >= 2;      // opt-in: measured no faster than one CTA (profiles/README.md)
-      if (use_cluster) {
-        int ncl = ctx->n_sm / 2; if (ncl > npend) ncl = npend; if (ncl > ctx->ws_slots) ncl = ctx->ws_slots;
-        ctx->wide_block = 1024;        // reported as 2 x 512
-        k_search_pipe2<512><<<2 * ncl, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
-      }
-      else if (pipe && which == 0) k_search_pipe<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
+      if (pipe && which == 0) k_search_pipe<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
       else if (pipe && which == 1) k_search_pipe<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
       else if (pipe && which == 2) k_search_pipe<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
       else if (which == 0) k_search<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);

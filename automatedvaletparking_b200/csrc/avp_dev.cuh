@@ -69,7 +69,8 @@ __device__ __noinline__ double py_hypot(double a, double b) {
   if (isnan(v0) || isnan(v1)) return NAN;
   if (mx == 0.0) return mx;
   int max_e; frexp(mx, &max_e);
-  if (max_e < -1023) return 2.2250738585072014e-308 * py_hypot(v0 / 2.2250738585072014e-308, v1 / 2.2250738585072014e-308);
+  const bool tiny = max_e < -1023;           // ldexp(1.0, -max_e) would overflow: vector_norm rescales by DBL_MIN and calls itself once
+  if (tiny) { v0 = v0 / 2.2250738585072014e-308; v1 = v1 / 2.2250738585072014e-308; mx = v0 > v1 ? v0 : v1; frexp(mx, &max_e); }
   double scale = ldexp(1.0, -max_e), csum = 1.0, frac1 = 0.0, frac2 = 0.0, x, h;
   dl_t pr, sm;
   x = v0 * scale; pr = dl_mul(x, x); sm = dl_fast_sum(csum, pr.hi); csum = sm.hi; frac1 += pr.lo; frac2 += sm.lo;
@@ -78,15 +79,16 @@ __device__ __noinline__ double py_hypot(double a, double b) {
   pr = dl_mul(-h, h); sm = dl_fast_sum(csum, pr.hi); csum = sm.hi; frac1 += pr.lo; frac2 += sm.lo;
   x = csum - 1.0 + (frac1 + frac2);
   h += x / (2.0 * h);
-  return h / scale;
+  return tiny ? 2.2250738585072014e-308 * (h / scale) : h / scale;
 }
 
 // Python float % (Objects/floatobject.c float_rem); fmod is exact
 // fmod(v, w) for w > 0, exact: each subtraction below is exact by Sterbenz' lemma
 // (r in [k*w, 2*k*w] minus k*w, k a power of two), so the result equals the exact remainder.
+__device__ __noinline__ double fmod_big(double v, double w) { return fmod(v, w); }      // out of line: every rs_M would carry a copy
 __device__ __forceinline__ double fmod_small(double v, double w) {
   double r = fabs(v);
-  if (r >= 8.0 * w) return fmod(v, w);
+  if (r >= 8.0 * w) return fmod_big(v, w);
   if (r >= 4.0 * w) r -= 4.0 * w;
   if (r >= 2.0 * w) r -= 2.0 * w;
   if (r >= w) r -= w;
@@ -189,7 +191,6 @@ __device__ __forceinline__ void veh_geom(const avp_config &c, double x, double y
   double d1 = (l == 0) ? g.vb[0][1] - g.vb[3][1] : g.vb[3][1] - g.vb[2][1];
   const double side = sqrt(d0 * d0 + d1 * d1);
   g.v_lb = shfl_dbl(side, 0); g.v_len = shfl_dbl(side, 1);
-#pragma unroll
   const double ils = 1.0 / ls;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { g.lk[i] = shfl_dbl(lk, i); g.lb[i] = shfl_dbl(lb, i); g.ls[i] = shfl_dbl(ls, i); g.ils[i] = shfl_dbl(ils, i); }
@@ -276,6 +277,67 @@ __device__ __forceinline__ bool check_distance_warp(const avp_config &c, const S
   return hit;
 }
 
+// The same check with the vehicle geometry in SHARED memory (one VehGeom per warp, `sg`): lanes 0..3 compute
+// corner l / boundary line l / one bound of the AABB each and store them; every lane reads what it needs.
+// Same IEEE operations as veh_geom, but no shuffles (veh_geom: 40 per pose) and no 32 doubles of geometry
+// live in registers across the cell loop (under a 128-register cap the compiler re-derived the AABB from the
+// corners in every iteration: 12 % of the pipelined kernel's instructions).
+__device__ __forceinline__ void veh_geom_sm(const avp_config &c, double x, double y, double cs, double sn, VehGeom *sg) {
+  const int lane = threadIdx.x & 31, l = lane & 3;
+  __syncwarp();                                   // the previous pose's readers are done
+  if (lane < 4) {
+    const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
+    const double lx0 = -c.lr - fr, lx1 = c.lw + c.lf + fr, ly0 = -c.lb / 2 - sd, ly1 = c.lb / 2 + sd;
+    const double locx = (l == 0 || l == 3) ? lx0 : lx1, locy = (l < 2) ? ly0 : ly1;
+    const double cx = __fma_rn(-sn, locy, cs * locx) + x;      // as veh_geom
+    const double cy = __fma_rn(cs, locy, sn * locx) + y;
+    sg->vb[l][0] = cx; sg->vb[l][1] = cy;
+    if (l == 0) { sg->vb[4][0] = cx; sg->vb[4][1] = cy; }
+  }
+  __syncwarp();
+  if (lane < 4) {
+    const double p1x = sg->vb[l][0], p1y = sg->vb[l][1], p2x = sg->vb[l + 1][0], p2y = sg->vb[l + 1][1];   // vb[4] = vb[0]
+    const double lk = (p2y - p1y) / (p2x - p1x);
+    const double lb = p1y - lk * p1x;
+    const double ls = sqrt(1 + lk * lk);
+    sg->lk[l] = lk; sg->lb[l] = lb; sg->ls[l] = ls; sg->ils[l] = 1.0 / ls;
+    if (l < 2) {                                  // the two side lengths (collision_check.py:165-169)
+      const double d0 = (l == 0) ? sg->vb[0][0] - sg->vb[3][0] : sg->vb[3][0] - sg->vb[2][0];
+      const double d1 = (l == 0) ? sg->vb[0][1] - sg->vb[3][1] : sg->vb[3][1] - sg->vb[2][1];
+      const double side = sqrt(d0 * d0 + d1 * d1);
+      if (l == 0) sg->v_lb = side; else sg->v_len = side;
+    }
+    // lane 0: x_min, 1: x_max, 2: y_min, 3: y_max -- the strict compare chain of veh_geom over corners 1..4
+    const int dim = l >> 1; const bool want_max = (l & 1) != 0;
+    double v = sg->vb[0][dim];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) { const double w = sg->vb[i][dim]; if (want_max ? (w > v) : (w < v)) v = w; }
+    if (l == 0) sg->x_min = v; else if (l == 1) sg->x_max = v; else if (l == 2) sg->y_min = v; else sg->y_max = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ bool check_distance_warp_sm(const avp_config &c, const ScenDev &S, const double2 *cells,
+                                                       const int32_t *col_start, double x, double y, double cs, double sn, VehGeom *sg) {
+  const int lane = threadIdx.x & 31;
+  veh_geom_sm(c, x, y, cs, sn, sg);
+  const double x_min = sg->x_min, x_max = sg->x_max, y_min = sg->y_min, y_max = sg->y_max;
+  int lo, hi;
+  col_range(S, x_min, x_max, lo, hi);
+  if (lo > hi) return false;
+  const int beg = col_start[lo], end = col_start[hi + 1];
+  bool hit = false;
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    bool h = false;
+    if (i < end) {
+      const double2 p = cells[i];
+      if (p.x >= x_min && p.x <= x_max && p.y >= y_min && p.y <= y_max) h = cell_hits(*sg, p.x, p.y);
+    }
+    if (__any_sync(AVP_FULL_MASK, h)) { hit = true; break; }
+  }
+  return hit;
+}
+
 // two_circle_checker.check (collision_check.py:88-137), warp-collective
 __device__ __forceinline__ bool check_circle_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
                                                   double x, double y, double cs, double sn) {
@@ -307,6 +369,11 @@ __device__ __forceinline__ bool check_pose_cs_warp(const avp_config &c, const Sc
                                                    const int32_t *col_start, double x, double y, double cs, double sn) {
   return c.collision_mode == 1 ? check_circle_warp(c, S, cells, x, y, cs, sn)
                                : check_distance_warp(c, S, cells, col_start, x, y, cs, sn);
+}
+__device__ __forceinline__ bool check_pose_cs_warp_sm(const avp_config &c, const ScenDev &S, const double2 *cells,
+                                                      const int32_t *col_start, double x, double y, double cs, double sn, VehGeom *sg) {
+  return c.collision_mode == 1 ? check_circle_warp(c, S, cells, x, y, cs, sn)
+                               : check_distance_warp_sm(c, S, cells, col_start, x, y, cs, sn, sg);
 }
 __device__ __forceinline__ bool check_pose_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
                                                 const int32_t *col_start, double x, double y, double th) {
@@ -430,13 +497,16 @@ __device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double 
 
 // normalised query of generate_path (rs_curve.py:627-634)
 struct RsQuery { double x, y, phi, xb, yb, sp, cp; };   // sp, cp = sin(phi), cos(phi): sin(-phi) = -sp, cos(-phi) = cp bit for bit
-__device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
+// c, s = cos(q0[2]), sin(q0[2]) (callers that already hold them pass them in: same function, same argument, same bits)
+__device__ __forceinline__ void rs_query_cs(const double q0[3], double c, double s, const double q1[3], double maxc, RsQuery &Q) {
   const double dx = q1[0] - q0[0], dy = q1[1] - q0[1], dth = q1[2] - q0[2];
-  const double c = d_cos(q0[2]), s = d_sin(q0[2]);
   Q.x = (c * dx + s * dy) * maxc; Q.y = (-s * dx + c * dy) * maxc; Q.phi = dth;
   const double cp = d_cos(dth), sp = d_sin(dth);
   Q.sp = sp; Q.cp = cp;
   Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;          // rs_curve.py:286-287, :456-457
+}
+__device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
+  rs_query_cs(q0, d_cos(q0[2]), d_sin(q0[2]), q1, maxc, Q);
 }
 
 // one word instance -> (valid, t, u, v)

@@ -563,6 +563,18 @@ __device__ __forceinline__ int htab_find(const int32_t *htab, int mask, const No
   }
   return -1;
 }
+// the same probe issued by a warp other than the inserting one (the pipelined kernel's evaluators): the slot is read at L2
+// (ld.global.cg), where the inserts' atomicCAS operations are performed
+__device__ __forceinline__ int htab_find_cg(const int32_t *htab, int mask, const Node *nodes, double x, double y, double t) {
+  unsigned long long p = pose_hash(x, y, t);
+  for (int probes = 0; probes <= mask; ++probes, ++p) {
+    const int e = __ldcg(&htab[p & mask]);
+    if (e < 0) return -1;
+    const Node &n = nodes[e];
+    if (n.x == x && n.y == y && n.theta == t) return e;
+  }
+  return -1;
+}
 // concurrent insert (distinct poses): claim the first empty slot of the probe sequence
 __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node *nodes, int idx) {
   const Node &n = nodes[idx];

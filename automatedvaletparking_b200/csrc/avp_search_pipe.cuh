@@ -17,34 +17,42 @@
 // is not in the table yet (then the prediction may miss).  A miss costs one un-overlapped evaluation;
 // results never depend on the prediction (a PURE result is only used for the node it was computed for).
 //
-//   barrier A | C: accept the result of the popped node; lookups + node records (lanes 0..9);    | barrier B
-//             |    predict the next pop; publish it as the evaluators' target                    |
-//   barrier B | C: sequential commit in slot order (Dijkstra resumes inside), then heappop       | barrier A
-//             | E: successor poses -> rs words || course points -> selection, collision checks   |
-//             |    of the successors' sub-steps and of the course points (dynamic queue) -> combine
+//   barrier A | C: accept the result of the popped node; lookups (lanes 0..9, probes read ahead by    | barrier B
+//             |    the evaluators); predict the next pop; publish it as the evaluators' target and       |
+//             |    initialise their queue                                                             |
+//   barrier B | C: node records, sequential commit in slot order (Dijkstra resumes inside), heappop,  | barrier A
+//             |    then it takes E1 items if any are left                                             |
+//             | E: ONE dependency-ordered queue of warp items (see E1 / E2 below)                     |
 //
-// The evaluators synchronise among themselves with named barrier 1; A and B are __syncthreads().
+// The evaluation is a single queue of warp items without a barrier inside: items whose inputs come from
+// other items (rs words <- successor poses, sub-step checks <- sub-step poses, course point checks <-
+// course plan, word selection <- all rs items, table probes <- the commit warp's inserts) sit behind their
+// producers in the queue and wait on a shared-memory flag / counter (release / acquire at CTA scope).  A
+// producer never waits, so the queue cannot dead-lock.  A and B are __syncthreads(), the only barriers
+// of a pop.
 // The word of the goal shot is the word selected when the node was scored (NodeShot), so the shot costs
-// no rs solve; its course is planned while the successor poses are computed and its points are
-// collision-checked in the same queue as the successors' sub-steps.
+// no rs solve; its course is planned by the first queue item and its points are collision-checked by
+// whichever warps run out of rs / sub-step items first.
+// The exact-pose table probes and h-table reads of the NEXT commit's lookups are issued by the evaluators
+// (item 3) as soon as the running commit has finished its table inserts: the DRAM round trips of the
+// lookups leave the serial section between A and B (7-8 k -> 4.5 k cycles per pop).
 #pragma once
-#include <cooperative_groups.h>
 #include "avp_kernels.cuh"
-namespace cg = cooperative_groups;
 
 enum { CTL_FINISH = 2 };
 
 // The rs warp items of the E1 queue: up to three word instances per item (lanes = instance slot x successor), formed so
-// that a warp runs one word formula where possible (4 instances per family: 3 + 1 left over, the left-overs grouped by
-// shared code), and ordered longest first: the tau/omega families (LRLRn 18-21, LRLRp 22-25) as half-size items in front.
-#define RS_NITEM 17
+// that a warp runs one word formula where possible (4 instances per family: 3 + 1 left over).  Ordered by measured cost,
+// longest first (profiles/: 21 k ... 3 k cycles per item); a left-over item with three different formulas costs the sum of
+// the three (41 k cycles for {9,29,37}), so those instances are items of their own.
+#define RS_NITEM 19
 __device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
-  {18, 19, -1}, {20, 21, -1}, {22, 23, -1}, {24, 25, -1},
-  {6, 7, 8}, {26, 27, 28}, {34, 35, 36}, {42, 43, 44}, {9, 29, 37},
-  {10, 11, 12}, {14, 15, 16}, {45, 13, 17}, {2, 3, 4}, {30, 31, 32}, {38, 39, 40}, {5, 33, 41}, {0, 1, -1}};
+  {45, 13, 17}, {0, 1, -1}, {6, 7, 8}, {5, 33, 41}, {20, 21, -1}, {22, 23, -1}, {10, 11, 12}, {14, 15, 16}, {26, 27, 28},
+  {34, 35, 36}, {24, 25, -1}, {9, -1, -1}, {29, -1, -1}, {37, -1, -1}, {2, 3, 4}, {38, 39, 40}, {30, 31, 32}, {42, 43, 44}, {18, 19, -1}};
 
 struct PureRes {
   double cpose[AVP_NCHILD_MAX][3];
+  int32_t found[AVP_NCHILD_MAX], hv[AVP_NCHILD_MAX];     // exact-pose table probe and h-table value, read ahead by the evaluators (see E2)
   double rsL[AVP_NCHILD_MAX];
   NodeShot shot[AVP_NCHILD_MAX];
   int32_t coll[AVP_NCHILD_MAX], rsok[AVP_NCHILD_MAX], inrad[AVP_NCHILD_MAX], hid[AVP_NCHILD_MAX];
@@ -56,20 +64,27 @@ struct EvalTarget { double x, y, theta; NodeShot shot; int32_t node, in_radius, 
 // clock read that the compiler may not move across barriers or memory operations (profiling counters)
 __device__ __forceinline__ long long clock_ordered() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 
-template <int NTHREADS>
-__device__ __forceinline__ void eval_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-// CLUSTER: the kernel is launched as thread-block clusters of two CTAs (two SMs) per scenario.  CTA 0 is the CTA
-// described above; CTA 1 (the HELPER) takes the collision work of every evaluation -- the successors' sub-step
-// checks and the shot's course (plan, points, checks) -- and writes the flags into CTA 0's shared memory
-// (distributed shared memory); barriers A and B become cluster barriers.  Used when the scenarios of pass 2 fit
-// n_sm / 2 clusters: the evaluation is throughput bound on one SM (see profiles/), two SMs halve it.
-template <int BLOCK, bool CLUSTER>
+// CTA-scope release / acquire on shared-memory words: the hand-off between producers and consumers of the evaluators'
+// queue (the payload is written with plain stores before the release and read with plain loads after the acquire).
+__device__ __forceinline__ void st_release_cta(int *p, int v) { asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_cta(const int *p) { int v; asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory"); return v; }
+// wait until *p >= want.  A producer never waits (see the header), so this returns after a bounded time; the guard
+// (2^27 cycles, three orders of magnitude above any real wait) turns a protocol bug into an error status instead of a hang.
+__device__ __forceinline__ bool wait_ge_cta(const int *p, int want) {
+  if (ld_acquire_cta(p) >= want) return true;
+  const long long t0 = clock64();
+  for (int k = 1;; ++k) {
+    if (ld_acquire_cta(p) >= want) return true;
+    if ((k & 255) == 0 && clock64() - t0 > (1ll << 27)) return false;
+  }
+}
+__device__ __forceinline__ void add_release_cta(int *p, int v) { asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
+
+template <int BLOCK>
 __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   static_assert(BLOCK >= 128 && BLOCK % 32 == 0, "one commit warp + at least three evaluator warps");
-  constexpr int NWARPS = BLOCK / 32, NE = NWARPS - 1, ET = NE * 32;
   constexpr int SMO = avp_sm_open(BLOCK);
-  constexpr int SELW = NE >= 8 ? 4 : (NE >= 4 ? 2 : 1);   // evaluator warps that run the word selection before they join the collision queue
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double *s_of = reinterpret_cast<double *>(s_dyn);
   int32_t *s_oi = reinterpret_cast<int32_t *>(s_dyn + sizeof(double) * SMO);
@@ -90,16 +105,15 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   __shared__ int s_chit[AVP_NCHILD_MAX];
   __shared__ int s_scen, s_ctlA, s_ctlB, s_cur, s_do_commit, s_rb, s_nplan, s_npts, s_shot_coll, s_shot_bad, s_work;
   __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls, s_on, s_in_radius, s_best_ok;
+  __shared__ int s_work2, s_work3, s_rs_done, s_course_rdy, s_q_rdy, s_sub_rdy, s_ins_done, s_cstride;   // the evaluators' queue: tail counter, finished rs items, course / rs queries / sub-step poses published, table inserts of the running commit done, stride of the course point order
+  __shared__ VehGeom s_vg[BLOCK / 32];           // per warp: the vehicle rectangle of the pose being checked (check_distance_warp_sm)
   __shared__ DijCtx s_D;
+  __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts), development aid
   __shared__ long long s_wp[BLOCK / 32][8];   // per warp: cycles lane 0 spent working in each evaluator phase (barrier waits excluded)
 
   const avp_config &cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int etid = tid - 32, ewarp = warp - 1;
-  const int slot = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int rank = CLUSTER ? (int)(blockIdx.x & 1) : 0;          // cluster dims (2,1,1): rank in cluster = blockIdx.x & 1
-  cg::cluster_group cluster = cg::this_cluster();
-#define SYNC_AB() do { if (CLUSTER) cluster.sync(); else __syncthreads(); } while (0)
+  const int slot = (int)blockIdx.x;
   const int nchild = 2 * cfg.steering_angle_num;
   const double maxc = 1 / cfg.min_radius_turn;
   Node *nodes = P.nodes + (size_t)slot * P.node_cap;
@@ -111,152 +125,14 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
 
   for (;;) {
-    if (rank == 0 && tid == 0) s_scen = atomicAdd(P.work_counter, 1);
-    SYNC_AB();
-    const int scen_i = (CLUSTER && rank == 1) ? *cluster.map_shared_rank(&s_scen, 0) : s_scen;
+    if (tid == 0) s_scen = atomicAdd(P.work_counter, 1);
+    __syncthreads();
+    const int scen_i = s_scen;
     if (scen_i >= P.n_work) break;
     const int sc = P.work_list ? P.work_list[scen_i] : scen_i;
     const ScenDev &S = P.scen[sc];
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
-    if (CLUSTER && rank == 1) {
-      // =========================== HELPER CTA (cluster rank 1) ===========================
-      // Every step: barrier A -> read CTA 0's exit word -> barrier B -> read the target -> sub-step poses ->
-      // one queue: [0] the shot's course plan + points, [1..nchild] one successor's sub-step checks each,
-      // [nchild+1 ..] the course points' checks (they wait for item 0) -> flags to CTA 0's shared memory.
-      const int *r_ctlA = cluster.map_shared_rank(&s_ctlA, 0), *r_ctlB = cluster.map_shared_rank(&s_ctlB, 0);
-      const EvalTarget *r_tgt = cluster.map_shared_rank(&s_tgt, 0);
-      int *r_chit = cluster.map_shared_rank(&s_chit[0], 0), *r_scoll = cluster.map_shared_rank(&s_shot_coll, 0), *r_sbad = cluster.map_shared_rank(&s_shot_bad, 0);
-      for (;;) {
-        cluster.sync();                            // A
-        if (*r_ctlA == CTL_EXIT) break;
-        cluster.sync();                            // B
-        if (*r_ctlB != CTL_RUN) break;
-        if (tid < (int)(sizeof(EvalTarget) / 8)) reinterpret_cast<long long *>(&s_tgt)[tid] = reinterpret_cast<const long long *>(r_tgt)[tid];
-        if (tid == 32) { s_shot_coll = 0; s_shot_bad = 0; s_nplan = 0; s_work = 0; s_npts = -1; }
-        if (tid >= 64 && tid < 64 + nchild) s_chit[tid - 64] = 0;
-        __syncthreads();
-        const EvalTarget T = s_tgt;
-        if (T.valid) {
-          const int phi_np = !T.is_root;
-          const int nsubs = cfg.n_substeps;
-          {
-            const int nsub = nsubs <= 4 ? nsubs : 4;
-            for (int item = warp + NWARPS * lane; item < nchild * nsub; item += NWARPS * 32) {
-              const int i = item / nsub, k = item % nsub;
-              const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-              const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-              const double td_i = speed * cfg.ddt * (k + 1);
-              const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-              const double cs = d_cos(th_i), sn = d_sin(th_i);
-              s_sub[i][k][0] = T.x + td_i * cs; s_sub[i][k][1] = T.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
-            }
-          }
-          __syncthreads();
-          for (;;) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&s_work, 1);
-            it = __shfl_sync(AVP_FULL_MASK, it, 0);
-            if (it == 0) {
-              int npts = 0;
-              if (T.in_radius) {
-                if (lane == 0) {
-                  RsBest b; b.ok = 0; b.degenerate = 0; b.n = 0; b.ct = 0; b.L = 0.0; b.inst = -1;
-                  if (!T.shot.ok) s_shot_bad = 1;
-                  else {
-                    unsigned mask;
-                    b.ok = 1; b.inst = T.shot.inst; b.L = T.shot.L;
-                    b.n = rs_arrange(T.shot.inst, T.shot.t, T.shot.u, T.shot.v, 1, phi_np, b.len, b.ct, mask);
-                    if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
-                  }
-                  s_best = b;
-                  s_tcs[0] = d_cos(-T.theta); s_tcs[1] = d_sin(-T.theta);
-                }
-                __syncwarp();
-                if (!s_shot_bad) {
-                  const int nseg = s_best.n;
-                  const char *mode = rs_ct_names[s_best.ct];
-                  if (lane < nseg) {
-                    double oyaw = 0.0;
-                    for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
-                    double ix, iy, yaw_next = oyaw; int dir;
-                    rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
-                    s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;
-                  }
-                  __syncwarp();
-                  if (lane == 0) {
-                    const double step = 0.5 * maxc;
-                    s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
-                    for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
-                    int ind = 1; double d, pd, ll = 0.0;
-                    CYAW[0] = 0.0; CDIR[0] = -1;
-                    for (int i = 0; i < nseg; ++i) {
-                      const double l = s_best.len[i];
-                      d = (l > 0.0) ? step : -step;
-                      ind -= 1;
-                      if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
-                      while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
-                      if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
-                      ll = l - pd - d;
-                      ind += 1; CYAW[ind] = l; CDIR[ind] = i;
-                    }
-                    s_nplan = ind + 1;
-                  }
-                  __syncwarp();
-                  if (!s_shot_bad) {
-                    const int nplan = s_nplan;
-                    for (int j = lane; j < nplan; j += 32) {
-                      if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
-                      const int seg = CDIR[j]; const double l = CYAW[j];
-                      double px, py, pyaw = 0.0; int dir;
-                      rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
-                      if (mode[seg] == 'S') pyaw = s_org[seg][2];
-                      CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
-                    }
-                    __syncwarp();
-                    if (lane == 0) { int n = nplan; while (n > 0 && CX[n - 1] == 0.0) --n; npts = n; }     // rs_curve.py:588-592
-                  }
-                }
-              }
-              __syncwarp();
-              if (lane == 0) { __threadfence_block(); *(volatile int *)&s_npts = npts; }      // publishes the course: the check items may start
-            } else if (it <= nchild) {
-              const int i = it - 1;
-              int coll = 0;
-              for (int k = 0; k < nsubs; ++k) {
-                bool hit;
-                if (k < 4) hit = check_pose_cs_warp(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3]);
-                else {
-                  const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-                  const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-                  const double td_i = speed * cfg.ddt * (k + 1);
-                  const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-                  hit = check_pose_warp(cfg, S, cells, col_start, T.x + td_i * d_cos(th_i), T.y + td_i * d_sin(th_i), th_i);
-                }
-                if (hit) { coll = 1; break; }
-              }
-              if (lane == 0) s_chit[i] = coll;
-            } else {
-              int npts = 0;
-              if (lane == 0) { while ((npts = *(volatile int *)&s_npts) < 0) __nanosleep(200); }
-              npts = __shfl_sync(AVP_FULL_MASK, npts, 0);
-              const int j = it - 1 - nchild;
-              if (j >= npts) break;
-              const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);
-              if (stop) continue;
-              const double ix = CX[j], iy = CY[j], cm = s_tcs[0], sm = s_tcs[1];
-              const double gx_ = cm * ix + sm * iy + T.x, gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
-              const double gyaw = pi_2_pi(CYAW[j] + T.theta);
-              if (check_pose_warp(cfg, S, cells, col_start, gx_, gy_, pi_2_pi(gyaw))) { if (lane == 0) s_shot_coll = 1; }
-            }
-          }
-        }
-        __syncthreads();
-        if (tid < nchild) r_chit[tid] = s_chit[tid];
-        if (tid == 32) { *r_scoll = s_shot_coll; *r_sbad = s_shot_bad; }
-      }
-      continue;                                    // next scenario
-    }
     int32_t *hval = P.hval + S.id_off, *ost = P.ost + S.id_off;
     const double goal[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
     int32_t *pops = P.pops ? P.pops + (size_t)sc * P.cap_pops : nullptr;
@@ -270,6 +146,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
 #define WP_START() do { if (lane == 0) wt = clock_ordered(); } while (0)
 #define WP_ACC(k) do { if (lane == 0) { const long long t_ = clock_ordered(); s_wp[warp][k] += t_ - wt; wt = t_; } } while (0)
     if (lane == 0) for (int k = 0; k < 8; ++k) s_wp[warp][k] = 0;
+    if (tid < 48) s_ic[tid] = 0;
     // timeline of ONE pop (the AVP_TRACE_POP-th of the scenario): absolute clocks of every warp at the phase boundaries
     long long *tsw = (P.wprof && warp < 16) ? P.wprof + ((size_t)sc * 16 + warp) * 24 + 8 : nullptr;
 #define TS(k) do { __syncwarp(); if (lane == 0 && tsw && ((k) < 2 ? (s_npops == P.trace_pop) : s_trace_on)) tsw[k] = clock_ordered(); } while (0)
@@ -343,7 +220,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
 
     bool reached = false;
     for (;;) {
-      SYNC_AB();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
+      __syncthreads();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
       PIPE_TICK(0, 4);                           // commit warp waiting for the evaluators
       TS(0);
       // s_ctlA is written by do_pop (between B and A) and read here; s_ctlB is written between A and B and read
@@ -370,10 +247,17 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
             if (lane < nchild) {
               const int i = lane;
               const int id = R.hid[i];
-              const int hvp = (id >= 0) ? hval[id] : -1;                  // issued first: overlaps the table probes
+              // probe and h value were read ahead by the evaluators (E2) after the table inserts of the commit that ran beside
+              // them: no insert and no Dijkstra resume has happened since, except that an h value missing then may be there now
+              int hvp = R.hv[i];
+              if (hvp < 0 && id >= 0) hvp = hval[id];
               const Node cn = nodes[cur];
               const double x_ = R.cpose[i][0], y_ = R.cpose[i][1], th = R.cpose[i][2];
+#ifdef AVP_NO_LOOKAHEAD
               found = htab_find(htab, hmask, nodes, x_, y_, th);
+#else
+              found = R.found[i];
+#endif
               const bool in_closed = found >= 0 && nodes[found].in_closed;
               const bool oob = (s_nclosed > 0) && (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
               skip = (in_closed || oob) ? 1 : 0;
@@ -423,15 +307,29 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
           EvalTarget T; T.valid = 1; T.node = cur; T.x = n.x; T.y = n.y; T.theta = n.theta; T.in_radius = n.in_radius; T.is_root = (cur == 0); T.shot = nshot[cur];
           s_tgt = T; s_do_commit = 0; pc[6]++;
         }
+        // ---- the evaluators' queue for the target just published: counters, flags, header of the result buffer
+        //      (the flags of the evaluation just finished were read above)
+        __syncwarp();
+        if (s_ctlB == CTL_RUN) {
+          if (lane < nchild) { s_valid[lane] = 0ull; s_chit[lane] = 0; }
+          if (lane == 0) {
+            s_nplan = 0; s_npts = 0; s_cstride = 1; s_work = 0; s_work2 = 0; s_work3 = 0; s_rs_done = 0; s_course_rdy = 0; s_q_rdy = 0; s_sub_rdy = 0;
+            s_ins_done = 0; s_shot_coll = 0; s_shot_bad = 0;
+            PureRes &Wn = s_res[s_rb ^ 1];
+            Wn.node = s_tgt.valid ? s_tgt.node : -1; Wn.in_radius = s_tgt.in_radius; Wn.shot_ok = (s_tgt.in_radius && s_tgt.shot.ok) ? 1 : 0;
+          }
+        }
       }
       if (warp == 0) WP_ACC(0);
       PIPE_TICK(0, 1);                           // accept + lookups + prediction
       TS(1);
-      SYNC_AB();                                 // ---- barrier B: target published
+      __syncthreads();                                 // ---- barrier B: target published
       TS(2);
       PIPE_TICK(32, 15);                         // evaluators waiting for the target
       if (s_ctlB != CTL_RUN) { reached = (s_ctlB == CTL_FINISH); break; }
 
+      EvalTarget T;
+      PureRes &W = s_res[s_rb ^ 1];                // s_rb only changes between A and B
       if (warp == 0) {
         // =========================== COMMIT warp ===========================
         WP_START();
@@ -457,6 +355,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
           }
           __syncwarp();
         }
+        if (lane == 0) { __threadfence_block(); st_release_cta(&s_ins_done, 1); }      // the evaluators may probe the table now
         if (s_do_commit && s_status == 0) {
           const PureRes &R = s_res[s_rb];
           const int cur = s_cur;
@@ -526,66 +425,43 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         WP_ACC(2);
         TS(4);
         PIPE_TICK(0, 3);                         // heappop
+        // ---- the commit warp joins the evaluators' queue (initialised before barrier B)
+        __syncwarp();
+        T = s_tgt;
+        if (!T.valid) continue;
+        WP_START();
       } else {
         // =========================== EVALUATORS ===========================
-        const EvalTarget T = s_tgt;
-        PureRes &W = s_res[s_rb ^ 1];
-        if (!T.valid) { if (etid == 0) W.node = -1; continue; }
+        T = s_tgt;
+        if (!T.valid) continue;
+        WP_START();
+        TS(3); TS(4);
+      }
+      // =========================== the evaluation queue (evaluators; the commit warp when it is done) ===========================
+      // ---- E1: the producers and the items that only need the successor poses:
+      //   0                      the shot's course from the node's stored word: plan (generate_local_course, rs_curve.py:537-594)
+      //                          and points in the local frame (:597-624); publishes s_npts / s_cstride, then s_course_rdy
+      //   1                      successor poses with their normalised rs queries (hybrid_a_star.py:145-151); publishes s_q_rdy
+      //   2                      sub-step poses (:185-194); publishes s_sub_rdy
+      //   3                      per successor (lanes): in_radius, cell id, and the read-ahead for the commit warp's lookups
+      //                          (exact-pose table probe, h-table value), after s_q_rdy and s_ins_done
+      //   4 .. 3+RS_NITEM        rs word instances (rs_item_inst: up to three instances x all successors per warp item), after
+      //                          s_q_rdy; each finished item adds one to s_rs_done
+      //   4+RS_NITEM ..          the successors' sub-step collision checks (:185-204), one successor each, after s_sub_rdy
+      {
         const int phi_np = !T.is_root;             // the root's theta is a Python float (see oracle generate_path)
         const int nsubs = cfg.n_substeps;
-        WP_START();
-        // ---- E0: successor poses with their normalised rs queries, and sub-step poses (hybrid_a_star.py:145-151, :185-194),
-        //          spread over the warps (one or two code paths per warp)
-        if (etid == 0) {
-          s_nplan = 0; s_work = 0;
-          if (!CLUSTER) { s_shot_coll = 0; s_shot_bad = 0; }       // cluster mode: the helper CTA owns these flags and s_chit
-          for (int i = 0; i < nchild; ++i) { s_valid[i] = 0ull; if (!CLUSTER) s_chit[i] = 0; }
-        }
-        {
-          const int nsub = CLUSTER ? 0 : (nsubs <= 4 ? nsubs : 4);
-          for (int item = ewarp + NE * lane; item < nchild + nchild * nsub; item += NE * 32) {
-            if (item < nchild) {
-              const int c = item;
-              double q0[3];
-              const double tn = cfg.tan_steer[c % cfg.steering_angle_num];
-              const double speed = (c < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-              const double td = speed * cfg.dt;
-              q0[2] = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
-              q0[0] = T.x + td * d_cos(q0[2]); q0[1] = T.y + td * d_sin(q0[2]);
-              W.cpose[c][0] = q0[0]; W.cpose[c][1] = q0[1]; W.cpose[c][2] = q0[2];
-              rs_query(q0, goal, maxc, s_Q[c]);
-            } else {
-              const int nsd = nsub > 0 ? nsub : 1, i = (item - nchild) / nsd, k = (item - nchild) % nsd;
-              const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-              const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-              const double td_i = speed * cfg.ddt * (k + 1);
-              const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-              const double cs = d_cos(th_i), sn = d_sin(th_i);
-              s_sub[i][k][0] = T.x + td_i * cs; s_sub[i][k][1] = T.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
-            }
-          }
-        }
-        WP_ACC(0);
-        TS(3);
-        eval_barrier<ET>();
-        TS(4);
-        WP_START();
-        PIPE_TICK(32, 7);                          // E0
-        // ---- E1: one queue of warp items, longest first:
-        //   0                      the shot's course from the node's stored word: plan (generate_local_course, rs_curve.py:537-594)
-        //                          and points in the local frame (:597-624)
-        //   1 .. RS_NITEM          rs word instances (rs_item_inst: up to three instances x all successors per warp item)
-        //   RS_NITEM+1 ..          the successors' sub-step collision checks (hybrid_a_star.py:185-204), one successor each
-        {
-          const int n_items = CLUSTER ? RS_NITEM : 1 + RS_NITEM + nchild;       // cluster mode: the helper CTA has items 0 and RS_NITEM+1..
-          for (;;) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&s_work, 1);
-            it = __shfl_sync(AVP_FULL_MASK, it, 0);
-            if (it >= n_items) break;
-            if (CLUSTER) it += 1;
-            if (it == 0) {
-              if (!T.in_radius) continue;
+        const int n_items = 4 + RS_NITEM + nchild;
+        VehGeom *vg = &s_vg[warp];
+        for (;;) {
+          int it = 0;
+          if (lane == 0) it = atomicAdd(&s_work, 1);
+          it = __shfl_sync(AVP_FULL_MASK, it, 0);
+          if (it >= n_items) break;
+          const long long ti_ = clock64();
+          if (it == 0) {
+            int npts = 0;
+            if (T.in_radius) {
               if (lane == 0) {
                 RsBest b; b.ok = 0; b.degenerate = 0; b.n = 0; b.ct = 0; b.L = 0.0; b.inst = -1;
                 if (!T.shot.ok) s_shot_bad = 1;
@@ -599,139 +475,212 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
                 s_tcs[0] = d_cos(-T.theta); s_tcs[1] = d_sin(-T.theta);
               }
               __syncwarp();
-              if (s_shot_bad) continue;
-              const int nseg = s_best.n;
-              const char *mode = rs_ct_names[s_best.ct];
-              if (lane < nseg) {
-                double oyaw = 0.0;                                        // heading at the start of segment `lane`
-                for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
-                double ix, iy, yaw_next = oyaw; int dir;
-                rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
-                s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;    // increments for now
-              }
-              __syncwarp();
-              if (lane == 0) {
-                const double step = 0.5 * maxc;
-                s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
-                for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
-                int ind = 1; double d, pd, ll = 0.0;
-                CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
-                for (int i = 0; i < nseg; ++i) {
-                  const double l = s_best.len[i];
-                  d = (l > 0.0) ? step : -step;
-                  ind -= 1;
-                  if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
-                  while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
-                  if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
-                  ll = l - pd - d;
-                  ind += 1; CYAW[ind] = l; CDIR[ind] = i;
+              if (!s_shot_bad) {
+                const int nseg = s_best.n;
+                const char *mode = rs_ct_names[s_best.ct];
+                if (lane < nseg) {
+                  double oyaw = 0.0;                                        // heading at the start of segment `lane`
+                  for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
+                  double ix, iy, yaw_next = oyaw; int dir;
+                  rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
+                  s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;    // increments for now
                 }
-                s_nplan = ind + 1;
-              }
-              __syncwarp();
-              if (s_shot_bad) continue;
-              const int nplan = s_nplan;
-              for (int j = lane; j < nplan; j += 32) {
-                if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
-                const int seg = CDIR[j]; const double l = CYAW[j];
-                double px, py, pyaw = 0.0; int dir;
-                rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
-                if (mode[seg] == 'S') pyaw = s_org[seg][2];
-                CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
-              }
-            } else if (it <= RS_NITEM) {
-              const int k = lane / nchild, row = lane - k * nchild;
-              const int inst = (k < 3) ? rs_item_inst[it - 1][k] : -1;
-              if (inst >= 0) {
-                double t, u, v;
-                if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
-                  RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
-                  c.L = rs_cand_L(inst, c, 1, 1);
-                  s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
+                __syncwarp();
+                if (lane == 0) {
+                  const double step = 0.5 * maxc;
+                  s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
+                  for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
+                  int ind = 1; double d, pd, ll = 0.0;
+                  CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
+                  for (int i = 0; i < nseg; ++i) {
+                    const double l = s_best.len[i];
+                    d = (l > 0.0) ? step : -step;
+                    ind -= 1;
+                    if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
+                    while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
+                    if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
+                    ll = l - pd - d;
+                    ind += 1; CYAW[ind] = l; CDIR[ind] = i;
+                  }
+                  s_nplan = ind + 1;
+                }
+                __syncwarp();
+                if (!s_shot_bad) {
+                  const int nplan = s_nplan;
+                  for (int j = lane; j < nplan; j += 32) {
+                    if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
+                    const int seg = CDIR[j]; const double l = CYAW[j];
+                    double px, py, pyaw = 0.0; int dir;
+                    rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
+                    if (mode[seg] == 'S') pyaw = s_org[seg][2];
+                    CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
+                  }
+                  __syncwarp();
+                  if (lane == 0) { int n = nplan; while (n > 0 && CX[n - 1] == 0.0) --n; npts = n; }     // trailing points with local x == 0.0 dropped (rs_curve.py:588-592)
                 }
               }
-            } else {
-              const int i = it - 1 - RS_NITEM;
-              int coll = 0;
-              for (int k = 0; k < nsubs; ++k) {
-                bool hit;
-                if (k < 4) hit = check_pose_cs_warp(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3]);
-                else {
-                  const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-                  const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-                  const double td_i = speed * cfg.ddt * (k + 1);
-                  const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-                  hit = check_pose_warp(cfg, S, cells, col_start, T.x + td_i * d_cos(th_i), T.y + td_i * d_sin(th_i), th_i);
-                }
-                if (hit) { coll = 1; break; }
-              }
-              if (lane == 0) s_chit[i] = coll;
             }
+            __syncwarp();
+            if (lane == 0) {
+              // the points are checked in the order (k * stride) mod npts, stride ~ 0.38 npts and coprime to npts: the node's own
+              // neighbourhood is free, so a colliding course is found after fewer checks than in path order (any hit decides)
+              int st = 1;
+#ifndef AVP_NO_CSTRIDE
+              if (npts > 4) { st = (npts * 49 + 64) >> 7; for (;;) { int a = npts, b = st; while (b) { const int t_ = a % b; a = b; b = t_; } if (a == 1) break; ++st; } }
+#endif
+              s_npts = npts; s_cstride = st; __threadfence_block(); st_release_cta(&s_course_rdy, 1);
+            }
+          } else if (it == 1) {
+            if (lane < nchild) {
+              const int c = lane;
+              double q0[3];
+              const double tn = cfg.tan_steer[c % cfg.steering_angle_num];
+              const double speed = (c < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+              const double td = speed * cfg.dt;
+              q0[2] = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
+              const double cs = d_cos(q0[2]), sn = d_sin(q0[2]);
+              q0[0] = T.x + td * cs; q0[1] = T.y + td * sn;
+              W.cpose[c][0] = q0[0]; W.cpose[c][1] = q0[1]; W.cpose[c][2] = q0[2];
+              rs_query_cs(q0, cs, sn, goal, maxc, s_Q[c]);
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); st_release_cta(&s_q_rdy, 1); }
+          } else if (it == 2) {
+            const int nsub = nsubs <= 4 ? nsubs : 4;
+            for (int item = lane; item < nchild * nsub; item += 32) {
+              const int i = item / nsub, k = item % nsub;
+              const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+              const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+              const double td_i = speed * cfg.ddt * (k + 1);
+              const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+              const double cs = d_cos(th_i), sn = d_sin(th_i);
+              s_sub[i][k][0] = T.x + td_i * cs; s_sub[i][k][1] = T.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); st_release_cta(&s_sub_rdy, 1); }
+          } else if (it == 3) {
+            if (!wait_ge_cta(&s_q_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+            if (lane < nchild) {
+              const int i = lane;
+              const double x_ = W.cpose[i][0], y_ = W.cpose[i][1];
+              W.inrad[i] = sqrt(d_pow2(x_ - goal[0]) + d_pow2(y_ - goal[1])) < cfg.flag_radius;       // hybrid_a_star.py:308-310
+              const long long id = map_index(S, x_, y_);
+              const int hid = (id >= 0 && id < S.n_ids) ? (int)id : -1;
+              W.hid[i] = hid;
+            }
+            // read ahead for the commit warp's lookups (hybrid_a_star.py:154-172, :272): the probe of the exact-pose table and the
+            // h-table value.  The table inserts of the commit running beside this evaluation are finished (s_ins_done) and nothing
+            // else is inserted before this result is used, so the probe is final; an h value can only change from missing to set.
+            int fnd = -1, hv = -1;
+#ifndef AVP_NO_LOOKAHEAD
+            if (!wait_ge_cta(&s_ins_done, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+            if (lane < nchild) {
+              const int hid = W.hid[lane];
+              if (hid >= 0) hv = *(volatile const int32_t *)&hval[hid];
+              fnd = htab_find_cg(htab, hmask, nodes, W.cpose[lane][0], W.cpose[lane][1], W.cpose[lane][2]);
+            }
+#endif
+            if (lane < nchild) { W.found[lane] = fnd; W.hv[lane] = hv; }
+          } else if (it <= 3 + RS_NITEM) {
+            if (!wait_ge_cta(&s_q_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+            const int k = lane / nchild, row = lane - k * nchild;
+            const int inst = (k < 3) ? rs_item_inst[it - 4][k] : -1;
+            if (inst >= 0) {
+              double t, u, v;
+              if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
+                RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
+                c.L = rs_cand_L(inst, c, 1, 1);
+                s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); add_release_cta(&s_rs_done, 1); }
+          } else {
+            if (!wait_ge_cta(&s_sub_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+            const int i = it - 4 - RS_NITEM;
+            int coll = 0;
+            for (int k = 0; k < nsubs; ++k) {
+              bool hit;
+              if (k < 4) hit = check_pose_cs_warp_sm(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3], vg);
+              else {
+                const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+                const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+                const double td_i = speed * cfg.ddt * (k + 1);
+                const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+                const double cs = d_cos(th_i), sn = d_sin(th_i);
+                hit = check_pose_cs_warp_sm(cfg, S, cells, col_start, T.x + td_i * cs, T.y + td_i * sn, cs, sn, vg);
+              }
+              if (hit) { coll = 1; break; }
+            }
+            if (lane == 0) s_chit[i] = coll;
           }
+          if (lane == 0 && it < 40) atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[it]), (unsigned long long)(clock64() - ti_));
         }
-        WP_ACC(1);
-        TS(5);
-        eval_barrier<ET>();
-        TS(6);
-        WP_START();
-        PIPE_TICK(32, 12);                         // E1
-        // ---- E2: a second queue:
-        //   0 .. nchild-1   per successor: set_path de-duplication + minimum per ctype group (lanes = groups), then lane 0:
-        //                   calc_optimal_path (combine the groups), the word kept for the successor's own shot, in_radius, cell id
-        //   nchild ..       collision checks of the shot's course points (hybrid_a_star.py:334-347; trailing points with
-        //                   local x == 0.0 dropped, rs_curve.py:588-592)
-        if (etid == 0) { W.node = T.node; W.in_radius = T.in_radius; W.shot_ok = (T.in_radius && T.shot.ok) ? 1 : 0; }
-        {
-          int npts = 0;
-          if (!CLUSTER && T.in_radius && !s_shot_bad) {
-            if (lane == 0) { int n = s_nplan; while (n > 0 && CX[n - 1] == 0.0) --n; npts = n; }
-            npts = __shfl_sync(AVP_FULL_MASK, npts, 0);
-          }
-          const int n_items = nchild + npts;
-          // s_work was left >= the E1 item count by every warp; the E2 counter continues from a common base
-          const int base = (CLUSTER ? RS_NITEM : 1 + RS_NITEM + nchild) + NE;
-          for (;;) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&s_work, 1) - base;
+        if (warp != 0) { WP_ACC(1); TS(5); WP_START(); PIPE_TICK(32, 12); }
+        // ---- E2: the items that consume other items' results:
+        //   course point checks (hybrid_a_star.py:334-347), after s_course_rdy, in strided order, skipped once one of them hit
+        //   word selection, two successors per warp item (lanes 0..10 / 16..26 = ctype groups): set_path de-duplication + minimum
+        //   per group, then calc_optimal_path (combine the groups) and the word kept for the successor's own shot; after every
+        //   rs item is finished (s_rs_done).  A warp takes a selection whenever the rs items are finished, else a course point.
+        // the commit warp only helps while E1 items are left: it arrives late, and a selection or a course point taken then
+        // would make it the last warp at barrier A
+        if (warp == 0) { WP_ACC(3); continue; }
+        if (!wait_ge_cta(&s_course_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; continue; }
+        const int npts = s_npts, cstride = s_cstride;
+        const int n_sel = (nchild + 1) / 2;
+        bool sel_left = true, chk_left = npts > 0;
+        for (;;) {
+          const long long ti_ = clock64();
+          int kind = -1, it = 0;                      // 0: selection, 1: course point
+          // the choice must be the same on every lane (the branches contain shuffles): lane 0 reads the counter
+          int rsd = 0;
+          if (lane == 0) rsd = ld_acquire_cta(&s_rs_done);
+          rsd = __shfl_sync(AVP_FULL_MASK, rsd, 0);
+          if (sel_left && (!chk_left || rsd >= RS_NITEM)) {
+            if (!wait_ge_cta(&s_rs_done, RS_NITEM)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+            if (lane == 0) it = atomicAdd(&s_work3, 1);
             it = __shfl_sync(AVP_FULL_MASK, it, 0);
-            if (it >= n_items) break;
-            if (it < nchild) {
-              const int i = it;
-              if (lane < RS_NGROUP) rs_select_group(s_cand[i], s_valid[i], lane, 1, 1, maxc, s_grp[i][lane]);
-              __syncwarp();
-              if (lane == 0) {
-                RsBest b; rs_combine_groups(s_grp[i], s_cand[i], 1, 1, b);
-                const int ok = (b.ok && !b.degenerate) ? 1 : 0;
-                W.rsok[i] = ok;
-                W.rsL[i] = b.ok ? b.L / maxc : 0.0;
-                NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
-                if (b.ok) { w.t = s_cand[i][b.inst].t; w.u = s_cand[i][b.inst].u; w.v = s_cand[i][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = ok; }
-                W.shot[i] = w;
-                const double x_ = W.cpose[i][0], y_ = W.cpose[i][1];
-                W.inrad[i] = sqrt(d_pow2(x_ - goal[0]) + d_pow2(y_ - goal[1])) < cfg.flag_radius;       // hybrid_a_star.py:308-310
-                const long long id = map_index(S, x_, y_);
-                W.hid[i] = (id >= 0 && id < S.n_ids) ? (int)id : -1;
-              }
-            } else {
-              const int j = it - nchild;
-              const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
-              if (stop) continue;
-              const double ix = CX[j], iy = CY[j], cm = s_tcs[0], sm = s_tcs[1];
-              const double gx_ = cm * ix + sm * iy + T.x, gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
-              const double gyaw = pi_2_pi(CYAW[j] + T.theta);
-              if (check_pose_warp(cfg, S, cells, col_start, gx_, gy_, pi_2_pi(gyaw))) { if (lane == 0) s_shot_coll = 1; }
+            if (it >= n_sel) { sel_left = false; continue; }
+            kind = 0;
+          } else if (chk_left) {
+            if (lane == 0) it = atomicAdd(&s_work2, 1);
+            it = __shfl_sync(AVP_FULL_MASK, it, 0);
+            if (it >= npts) { chk_left = false; continue; }
+            kind = 1;
+          } else break;
+          if (kind == 1) {
+            const int j = (int)(((long long)it * cstride) % npts);
+            const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
+            if (stop) { chk_left = false; continue; }
+            const double ix = CX[j], iy = CY[j], cm = s_tcs[0], sm = s_tcs[1];
+            const double gx_ = cm * ix + sm * iy + T.x, gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
+            const double gyaw = pi_2_pi(CYAW[j] + T.theta);
+            const double gth = pi_2_pi(gyaw);
+            if (check_pose_cs_warp_sm(cfg, S, cells, col_start, gx_, gy_, d_cos(gth), d_sin(gth), vg)) { if (lane == 0) s_shot_coll = 1; }
+          } else {
+            const int half = lane >> 4, gl = lane & 15, i = 2 * it + half;
+            if (i < nchild && gl < RS_NGROUP) rs_select_group(s_cand[i], s_valid[i], gl, 1, 1, maxc, s_grp[i][gl]);
+            __syncwarp();
+            if (i < nchild && gl == 0) {
+              RsBest b; rs_combine_groups(s_grp[i], s_cand[i], 1, 1, b);
+              const int ok = (b.ok && !b.degenerate) ? 1 : 0;
+              W.rsok[i] = ok;
+              W.rsL[i] = b.ok ? b.L / maxc : 0.0;
+              NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
+              if (b.ok) { w.t = s_cand[i][b.inst].t; w.u = s_cand[i][b.inst].u; w.v = s_cand[i][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = ok; }
+              W.shot[i] = w;
             }
           }
+          if (lane == 0) { const int k_ = 40 + kind; atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[k_]), (unsigned long long)(clock64() - ti_)); atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[k_ + 2]), 1ull); }
         }
-        WP_ACC(2);
-        TS(7);
-        PIPE_TICK(32, 13);                         // E2
+        WP_ACC(2); TS(7); PIPE_TICK(32, 13);
       }
     }
     __syncthreads();
 
     // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] = s_wp[warp][k]; }
+    if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] = s_ic[tid];
     if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] = pc[7]; o[12] = pc[12]; o[13] = pc[13]; o[14] = pc[14]; o[15] = pc[15]; }
     if (tid == 0) {
       avp_plan_summary &R = P.sums[sc];
@@ -785,12 +734,8 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
 #undef WP_START
 #undef WP_ACC
 #undef TS
-#undef SYNC_AB
-  if (CLUSTER) cluster.sync();        // a CTA's shared memory stays valid until its peer has read the last exit word
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) { search_pipe_body<BLOCK, false>(P); }
+__global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) { search_pipe_body<BLOCK>(P); }
 
-template <int BLOCK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BLOCK, 1) k_search_pipe2(KParams P) { search_pipe_body<BLOCK, true>(P); }

@@ -18,8 +18,8 @@ s = res.summaries
 print('search ms', ms, 'passes', dp.last_search_passes(), 'successors', res.successors)
 long_ = np.where(s['n_pops'] >= 20000)[0]
 mid = np.where((s['n_pops'] >= 1024) & (s['n_pops'] < 20000))[0]
-names = {0: 'C init+dij0', 1: 'C accept+lookups+predict', 2: 'C records+commit', 3: 'C heappop', 4: 'C wait for E',
-         7: 'E0 poses', 12: 'E1 course|rs|substep checks', 13: 'E2 select+combine|course checks', 15: 'E wait for C'}
+names = {0: 'C init+dij0', 1: 'C accept+lookups+predict', 2: 'C records+commit', 3: 'C heappop', 4: 'C queue help + wait for E',
+         7: 'E0 poses', 12: 'E1 course|rs|substep checks', 13: 'E2 course checks|select+combine', 15: 'E wait for C'}
 for nm, idx in (('long(20000 pops)', long_), ('mid(1024..20000)', mid)):
     if len(idx) == 0:
         continue
@@ -37,9 +37,9 @@ wp = dp.warp_profile()
 if len(long_):
     w = wp[long_][:, :, :8].astype(np.float64) / s['n_pops'][long_].astype(np.float64)[:, None, None]
     w = w.mean(0)
-    print('per-warp WORK cycles/pop (long scenarios; warp 0 = commit warp: lookups, commit, heappop): E0 E1 E2')
+    print('per-warp WORK cycles/pop (long scenarios; evaluators: E0 E1 E2 -; warp 0 = commit warp: lookups, commit, heappop, queue help)')
     for k in range(16):
-        print('  warp %2d  %7.0f %7.0f %7.0f' % (k, w[k, 0], w[k, 1], w[k, 2]))
+        print('  warp %2d  %7.0f %7.0f %7.0f %7.0f' % (k, w[k, 0], w[k, 1], w[k, 2], w[k, 3]))
 
 if os.environ.get('AVP_TRACE_POP') and len(long_):
     ev = ['afterA', 'arrB', 'afterB', 'arr1|Ccommit', 'aft1|Cpop', 'arr2', 'aft2', 'arrA']
@@ -49,3 +49,23 @@ if os.environ.get('AVP_TRACE_POP') and len(long_):
         print('timeline of pop %s, scenario %d (cycles since the first stamp): %s' % (os.environ['AVP_TRACE_POP'], sc_i, ' '.join(ev)))
         for k in range(16):
             print('  warp %2d ' % k + ' '.join('%7d' % (x - t0 if x > 0 else -1) for x in t[k]))
+
+if len(long_):
+    ic = wp[long_][:, :6, 16:24].reshape(len(long_), 48).astype(np.float64)
+    pops = s['n_pops'][long_].astype(np.float64)
+    m = (ic / pops[:, None]).mean(0)
+    print('queue items, cycles/pop (long scenarios): course %.0f  rs queries %.0f  sub-step poses %.0f  lookahead %.0f' % (m[0], m[1], m[2], m[3]))
+    print('  rs items   ' + ' '.join('%.0f' % x for x in m[4:23]))
+    print('  chains     ' + ' '.join('%.0f' % x for x in m[23:33]))
+    print('  selections (2 successors each) %.0f per pop, %.2f per pop, %.0f each | course checks %.0f per pop, %.2f per pop, %.0f each' %
+          (m[40], m[42], m[40] / max(m[42], 1e-9), m[41], m[43], m[41] / max(m[43], 1e-9)))
+
+# the scenarios that set the launch time: total cycles of the commit warp (init + phases 1..4), slowest first
+tot = pr[:, 0:5].sum(1).astype(np.float64)
+order = np.argsort(-tot)[:10]
+print('slowest scenarios (pass 2): scen pops Gcycles | per pop: lookups commit heappop help+wait | dijkstra/pop resumes pushes/pop init(Mcycles)')
+for i in order:
+    if s['n_pops'][i] < 1024:
+        continue
+    p = pr[i].astype(np.float64); n = float(s['n_pops'][i])
+    print('  %5d %6d %6.3f | %7.0f %7.0f %7.0f %7.0f | %7.0f %6d %5.2f %8.1f' % (i, n, tot[i] / 1e9, p[1] / n, p[2] / n, p[3] / n, p[4] / n, p[10] / n, p[11], p[9] / n, p[0] / 1e6))
