@@ -124,7 +124,7 @@ __device__ __forceinline__ double pi_2_pi(double th) {
   return th;
 }
 // rs_curve.py:669-680
-__device__ __forceinline__ double rs_M(double th) {
+__device__ __noinline__ double rs_M(double th) {
   double phi = py_mod(th, 2.0 * AVP_PI);
   if (phi < -AVP_PI) phi += 2.0 * AVP_PI;
   if (phi > AVP_PI) phi -= 2.0 * AVP_PI;
@@ -282,12 +282,17 @@ __device__ __forceinline__ bool check_distance_warp(const avp_config &c, const S
 // Same IEEE operations as veh_geom, but no shuffles (veh_geom: 40 per pose) and no 32 doubles of geometry
 // live in registers across the cell loop (under a 128-register cap the compiler re-derived the AABB from the
 // corners in every iteration: 12 % of the pipelined kernel's instructions).
-__device__ __forceinline__ void veh_geom_sm(const avp_config &c, double x, double y, double cs, double sn, VehGeom *sg) {
+// the inflated rectangle in the vehicle frame (create_anticlockpoint, costmap.py:85-121): passed by value to the out-of-line check
+struct VehDims { double lx0, lx1, ly0, ly1; };
+__device__ __forceinline__ VehDims veh_dims(const avp_config &c) {
+  const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
+  VehDims d; d.lx0 = -c.lr - fr; d.lx1 = c.lw + c.lf + fr; d.ly0 = -c.lb / 2 - sd; d.ly1 = c.lb / 2 + sd; return d;
+}
+__device__ __forceinline__ void veh_geom_sm(const VehDims vd, double x, double y, double cs, double sn, VehGeom *sg) {
   const int lane = threadIdx.x & 31, l = lane & 3;
   __syncwarp();                                   // the previous pose's readers are done
   if (lane < 4) {
-    const double fr = c.safe_fr_dis, sd = c.safe_side_dis;
-    const double lx0 = -c.lr - fr, lx1 = c.lw + c.lf + fr, ly0 = -c.lb / 2 - sd, ly1 = c.lb / 2 + sd;
+    const double lx0 = vd.lx0, lx1 = vd.lx1, ly0 = vd.ly0, ly1 = vd.ly1;
     const double locx = (l == 0 || l == 3) ? lx0 : lx1, locy = (l < 2) ? ly0 : ly1;
     const double cx = __fma_rn(-sn, locy, cs * locx) + x;      // as veh_geom
     const double cy = __fma_rn(cs, locy, sn * locx) + y;
@@ -316,10 +321,10 @@ __device__ __forceinline__ void veh_geom_sm(const avp_config &c, double x, doubl
   }
   __syncwarp();
 }
-__device__ __forceinline__ bool check_distance_warp_sm(const avp_config &c, const ScenDev &S, const double2 *cells,
-                                                       const int32_t *col_start, double x, double y, double cs, double sn, VehGeom *sg) {
+__device__ __noinline__ bool check_distance_warp_sm(const VehDims vd, const ScenDev &S, const double2 *cells,
+                                                    const int32_t *col_start, double x, double y, double cs, double sn, VehGeom *sg) {
   const int lane = threadIdx.x & 31;
-  veh_geom_sm(c, x, y, cs, sn, sg);
+  veh_geom_sm(vd, x, y, cs, sn, sg);
   const double x_min = sg->x_min, x_max = sg->x_max, y_min = sg->y_min, y_max = sg->y_max;
   int lo, hi;
   col_range(S, x_min, x_max, lo, hi);
@@ -373,7 +378,7 @@ __device__ __forceinline__ bool check_pose_cs_warp(const avp_config &c, const Sc
 __device__ __forceinline__ bool check_pose_cs_warp_sm(const avp_config &c, const ScenDev &S, const double2 *cells,
                                                       const int32_t *col_start, double x, double y, double cs, double sn, VehGeom *sg) {
   return c.collision_mode == 1 ? check_circle_warp(c, S, cells, x, y, cs, sn)
-                               : check_distance_warp_sm(c, S, cells, col_start, x, y, cs, sn, sg);
+                               : check_distance_warp_sm(veh_dims(c), S, cells, col_start, x, y, cs, sn, sg);
 }
 __device__ __forceinline__ bool check_pose_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
                                                 const int32_t *col_start, double x, double y, double th) {
@@ -530,7 +535,7 @@ __device__ __forceinline__ bool rs_eval_instance(int inst, const RsQuery &Q, dou
 }
 
 // instance -> (ctype id, lengths[], n, np-type mask); arrangement per rs_curve.py:200-534
-__device__ __forceinline__ int rs_arrange(int inst, double t, double u, double v, int xy_np, int phi_np,
+__device__ __noinline__ int rs_arrange(int inst, double t, double u, double v, int xy_np, int phi_np,
                                           double *l, int &ct, unsigned &mask) {
   const unsigned P = phi_np ? 1u : 0u;
   if (inst < 2) { l[0] = t; l[1] = u; l[2] = v; ct = inst ? CT_SRS : CT_SLS; mask = (xy_np ? 1u : 0u) | (P << 1); return 3; }
@@ -624,7 +629,7 @@ __device__ __forceinline__ void rs_select(RsCand *cand, unsigned long long valid
 }
 
 // rs_curve.py:597-624
-__device__ __forceinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
+__device__ __noinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
                                                double &px, double &py, double &pyaw, int &dir) {
   if (m == 'S') {
     px = ox + l / maxc * d_cos(oyaw); py = oy + l / maxc * d_sin(oyaw); pyaw = oyaw;
