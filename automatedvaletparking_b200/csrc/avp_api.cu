@@ -469,6 +469,14 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       // pass 2 runs the pipelined kernel (avp_search_pipe.cuh); AVP_PIPE=0 selects the phase-sequential k_search (A/B runs)
       const char *pe = getenv("AVP_PIPE");
       const bool pipe = which < 3 && !(pe && atoi(pe) == 0);
+      // the widest pipelined kernel is launched on every SM and one SM of each pair (TPC) takes the work (avp_search_pipe.cuh);
+      // AVP_SPREAD=0: one CTA per pending scenario, placed by the hardware (A/B runs)
+      const char *se = getenv("AVP_SPREAD");
+      // only while the pending scenarios (nearly) fit one per SM pair: two busy SMs of a pair are slower each but faster together
+      const bool spread = pipe && which == 0 && !(se && atoi(se) == 0) && ctx->ws_slots >= ctx->n_sm && ctx->n_sm >= 4 &&
+                          npend <= ctx->n_sm / 2 + ctx->n_sm / 8;
+      P.spread = spread ? 1 : 0;
+      if (spread) grid2 = ctx->n_sm;
       if (pipe && (ctx->nshot_slots < grid2 || ctx->nshot_node_cap != ctx->node_cap)) {
         free_dev(ctx->d_nshot); ctx->d_nshot = nullptr; ctx->nshot_slots = 0;
         const int ns = std::max(grid2, std::min(ctx->ws_slots, ctx->slots_w[0]));

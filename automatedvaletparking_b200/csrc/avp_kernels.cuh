@@ -73,6 +73,7 @@ struct KParams {
   int pop_budget;                 // pass 1: a scenario still searching after this many pops ends AVP_PENDING
   long long *prof;                // n * 16 SM-cycle accumulators / counters per scenario (thread 0): phases of the main loop, may be NULL
   int trace_pop;                  // pipelined kernel: the pop whose per-warp timeline is recorded in wprof (development aid)
+  int spread;                     // pipelined kernel: the grid covers every SM and the odd SM of each pair takes work only after the even ones (see avp_api.cu)
   long long *wprof;               // n * 16 * 24: per warp (16) and phase (8) work cycles of the pipelined kernel, may be NULL
   int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
   long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY

@@ -124,6 +124,32 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
   int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
 
+  // P.spread: the grid has one CTA per SM of the device although there is less work than SMs, and the CTAs on odd SM ids
+  // leave the work to the even ones: each scenario then has an SM pair (TPC) to itself.  The kernel is instruction-fetch
+  // bound and the pair shares fetch resources: a 20 000-pop scenario takes 1.43 G cycles with an idle neighbour SM, 1.9 G
+  // beside another such scenario (profiles/).  An odd CTA only watches the work counter: it leaves when every item is taken,
+  // and takes items itself if the counter has not moved for ~0.5 s (no even CTA resident, e.g. on a shared device).
+  if (P.spread) {
+    if (tid == 0) {
+      unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_));
+      int go = 1;
+      if (sm_ & 1u) {
+        go = 0;
+        long long t_last = clock64(); int last = -1;
+        for (;;) {
+          const int c = *(volatile int *)P.work_counter;
+          if (c >= P.n_work) break;
+          if (c != last) { last = c; t_last = clock64(); }
+          else if (clock64() - t_last > 1000000000ll) { go = 1; break; }
+          __nanosleep(20000);
+        }
+      }
+      s_scen = go;
+    }
+    __syncthreads();
+    if (!s_scen) return;
+    __syncthreads();
+  }
   for (;;) {
     if (tid == 0) s_scen = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -681,7 +707,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
     // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] = s_wp[warp][k]; }
     if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] = s_ic[tid];
-    if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] = pc[7]; o[12] = pc[12]; o[13] = pc[13]; o[14] = pc[14]; o[15] = pc[15]; }
+    if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] = pc[7]; o[12] = pc[12]; o[13] = pc[13]; { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); o[14] = ((long long)sm_ << 40) | (t_start & 0xffffffffffll); } o[15] = pc[15]; }     // o[14]: SM id and start clock (which scenarios shared a TPC, development aid)
     if (tid == 0) {
       avp_plan_summary &R = P.sums[sc];
       int status = s_status;

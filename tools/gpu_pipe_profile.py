@@ -69,3 +69,22 @@ for i in order:
         continue
     p = pr[i].astype(np.float64); n = float(s['n_pops'][i])
     print('  %5d %6d %6.3f | %7.0f %7.0f %7.0f %7.0f | %7.0f %6d %5.2f %8.1f' % (i, n, tot[i] / 1e9, p[1] / n, p[2] / n, p[3] / n, p[4] / n, p[10] / n, p[11], p[9] / n, p[0] / 1e6))
+
+# did a scenario share its TPC (SM pair 2k, 2k+1) with another long scenario?  o[14] = smid << 40 | start clock
+smid = (pr[:, 14] >> 40).astype(np.int64)
+in_p2 = s['n_pops'] >= 1024
+if len(long_):
+    host = {}
+    for i in np.where(in_p2)[0]:
+        host.setdefault(int(smid[i]), []).append(int(i))
+    rows = []
+    for i in long_:
+        sib = host.get(int(smid[i]) ^ 1, [])
+        sib_pops = sum(int(s['n_pops'][j]) for j in sib)
+        rows.append((tot[i] / 1e9, int(smid[i]), sib_pops))
+    rows.sort()
+    alone = [r[0] for r in rows if r[2] == 0]; part = [r[0] for r in rows if 0 < r[2] < 20000]; full = [r[0] for r in rows if r[2] >= 20000]
+    print('long scenarios by TPC sibling load (Gcycles mean / max / n): sibling idle %.3f %.3f %d | sibling mid %.3f %.3f %d | sibling long %.3f %.3f %d' % (
+        np.mean(alone) if alone else 0, max(alone) if alone else 0, len(alone), np.mean(part) if part else 0, max(part) if part else 0, len(part),
+        np.mean(full) if full else 0, max(full) if full else 0, len(full)))
+    print('  (Gcycles, smid, pops on the sibling SM): ' + ' '.join('%.2f/%d/%d' % r for r in rows))
