@@ -96,3 +96,22 @@ def test_sincos_port_is_bit_identical_to_libm(tmp_path):
     r = subprocess.run([str(exe), "1500000", "2024"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-500:]
     assert "sin mismatches 0, cos mismatches 0" in r.stdout
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "successors/s" and d["higher_is_better"] is True
+    assert d["metric"] == "collision-checked successor evaluations/sec" and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("Case1 obstacle map") and "model" not in d["config"]
