@@ -473,8 +473,9 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       // AVP_SPREAD=0: one CTA per pending scenario, placed by the hardware (A/B runs)
       const char *se = getenv("AVP_SPREAD");
       // only while the pending scenarios (nearly) fit one per SM pair: two busy SMs of a pair are slower each but faster together
+      // (break-even near 1.5 scenarios per pair on the bench recipe: measured at 90 pending, modelled from the pop counts of other seeds)
       const bool spread = pipe && which == 0 && !(se && atoi(se) == 0) && ctx->ws_slots >= ctx->n_sm && ctx->n_sm >= 4 &&
-                          npend <= ctx->n_sm / 2 + ctx->n_sm / 8;
+                          npend <= ctx->n_sm / 2 + ctx->n_sm / 4;
       P.spread = spread ? 1 : 0;
       if (spread) grid2 = ctx->n_sm;
       if (pipe && (ctx->nshot_slots < grid2 || ctx->nshot_node_cap != ctx->node_cap)) {
