@@ -99,6 +99,7 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   cudaFuncSetAttribute(k_search<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
   cudaFuncSetAttribute(k_search<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<AVP_BLOCK_NARROW>, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW)) != cudaSuccess || per_sm < 1) per_sm = 1;
+  { const char *ne = getenv("AVP_NARROW_PER_SM"); if (ne && atoi(ne) >= 1 && atoi(ne) < per_sm) per_sm = atoi(ne); }   // development aid: occupancy sweep of pass 1
   ctx->slots = ctx->n_sm * per_sm;               // persistent grids: multiples of the SM count
   int o = 0;
   ctx->slots_w[0] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<512>, 512, 12 * avp_sm_open(512)) == cudaSuccess && o > 0) ? o : 1);
@@ -475,7 +476,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
       // only while the pending scenarios (nearly) fit one per SM pair: two busy SMs of a pair are slower each but faster together
       // (break-even near 1.5 scenarios per pair on the bench recipe: measured at 90 pending, modelled from the pop counts of other seeds)
       const bool spread = pipe && which == 0 && !(se && atoi(se) == 0) && ctx->ws_slots >= ctx->n_sm && ctx->n_sm >= 4 &&
-                          npend <= ctx->n_sm / 2 + ctx->n_sm / 4;
+                          npend <= (getenv("AVP_SPREAD_MAX") ? atoi(getenv("AVP_SPREAD_MAX")) : ctx->n_sm / 2 + ctx->n_sm / 4);
       P.spread = spread ? 1 : 0;
       if (spread) grid2 = ctx->n_sm;
       if (pipe && (ctx->nshot_slots < grid2 || ctx->nshot_node_cap != ctx->node_cap)) {
