@@ -77,6 +77,9 @@ __device__ __forceinline__ bool wait_ge_cta(const int *p, int want) {
   for (int k = 1;; ++k) {
     if (ld_acquire_cta(p) >= want) return true;
     if ((k & 255) == 0 && clock64() - t0 > (1ll << 27)) return false;
+#ifdef AVP_SPIN_SLEEP        // A/B build: the polls are 8 % of the kernel's issued instructions (profiles/hot_footprint_r01d.txt)
+    __nanosleep(AVP_SPIN_SLEEP);
+#endif
   }
 }
 __device__ __forceinline__ void add_release_cta(int *p, int v) { asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
@@ -167,15 +170,28 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
     const long long t_start = clock64();
     // cycle accumulators: thread 0 (commit warp) and thread 32 (evaluators) each keep their own
     long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
+#ifdef AVP_NO_PROFILE        // A/B build without the cycle counters in the hot loop (the profile outputs stay zero)
+#define PIPE_TICK(who, k) do { } while (0)
+#else
 #define PIPE_TICK(who, k) do { if (tid == (who)) { const long long t_ = clock_ordered(); pc[k] += t_ - tp; tp = t_; } } while (0)
+#endif
     long long wt = 0;
+#ifdef AVP_NO_PROFILE
+#define WP_START() do { } while (0)
+#define WP_ACC(k) do { } while (0)
+#else
 #define WP_START() do { if (lane == 0) wt = clock_ordered(); } while (0)
 #define WP_ACC(k) do { if (lane == 0) { const long long t_ = clock_ordered(); s_wp[warp][k] += t_ - wt; wt = t_; } } while (0)
+#endif
     if (lane == 0) for (int k = 0; k < 8; ++k) s_wp[warp][k] = 0;
     if (tid < 48) s_ic[tid] = 0;
     // timeline of ONE pop (the AVP_TRACE_POP-th of the scenario): absolute clocks of every warp at the phase boundaries
     long long *tsw = (P.wprof && warp < 16) ? P.wprof + ((size_t)sc * 16 + warp) * 24 + 8 : nullptr;
+#ifdef AVP_NO_PROFILE
+#define TS(k) do { } while (0)
+#else
 #define TS(k) do { __syncwarp(); if (lane == 0 && tsw && ((k) < 2 ? (s_npops == P.trace_pop) : s_trace_on)) tsw[k] = clock_ordered(); } while (0)
+#endif
 
     // open_list.get() (path_planner.py:70) with the loop's exit tests; lane 0 of the commit warp
     auto do_pop = [&]() {
@@ -412,7 +428,11 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
                   Node &n = nodes[child];
                   const double f = s_g[i] + h;
                   n.h = h; n.f = f; n.in_open = 1;
+#ifdef AVP_NO_PROFILE
+                  oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child);
+#else
                   { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; }
+#endif
                 } else {                                                    // :219-230 (in place, no re-heapify)
                   const double new_f = h + s_g[i];
                   if (new_f < s_oldf[i]) {
@@ -640,7 +660,9 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
             }
             if (lane == 0) s_chit[i] = coll;
           }
+#ifndef AVP_NO_PROFILE
           if (lane == 0 && it < 40) atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[it]), (unsigned long long)(clock64() - ti_));
+#endif
         }
         if (warp != 0) { WP_ACC(1); TS(5); WP_START(); PIPE_TICK(32, 12); }
         // ---- E2: the items that consume other items' results:
@@ -697,7 +719,9 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
               W.shot[i] = w;
             }
           }
+#ifndef AVP_NO_PROFILE
           if (lane == 0) { const int k_ = 40 + kind; atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[k_]), (unsigned long long)(clock64() - ti_)); atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[k_ + 2]), 1ull); }
+#endif
         }
         WP_ACC(2); TS(7); PIPE_TICK(32, 13);
       }
