@@ -73,6 +73,7 @@ class DevicePlanner:
         if rc != 0 or not h:
             raise AvpError(f"avp_create failed (rc={rc}): no usable CUDA device {device}? this package has no CPU path")
         self._h = h
+        self.device = int(device)
         self.n = 0
         self.batch = None
         self.h2d_bytes = 0

@@ -16,18 +16,25 @@ class collision_checker:
         self._dev = None
 
     def _device(self):
+        """the device context whose derived avp_config (config AND vehicle) equals this checker's; the Map's own
+        context (default config, default Vehicle) is reused only when every field matches"""
         if self._dev is None:
-            want = dict(self.config) if self.config is not None else None
+            from ..batch import DevicePlanner
+            from ..hostcfg import make_avp_config
+            if self.config is None:
+                if self._mode == 'circle':
+                    raise ValueError("two_circle_checker needs a config (collision_check.py:88-92 reads config['safe_side_dis'])")
+                self._dev = self.map._device          # distance_checker(config=None): the reference only fails later, in check()
+                return self._dev
+            want = dict(self.config)
+            want['collision_check'] = self._mode
+            want['map_discrete_size'] = self.map.discrete_size
             base = self.map._device
-            same = want is None or (base.cfg.collision_mode == (1 if self._mode == 'circle' else 0)
-                                    and base.cfg.safe_side_dis == float(want['safe_side_dis']) and base.cfg.safe_fr_dis == float(want['safe_fr_dis']))
-            if same:
+            wcfg = make_avp_config(want, self.vehicle, max_pops=base.cfg.max_pops)
+            if bytes(wcfg) == bytes(base.cfg):
                 self._dev = base
-            else:                               # a context with this checker's mode / inflation
-                from ..batch import DevicePlanner
-                want['collision_check'] = self._mode
-                want['map_discrete_size'] = self.map.discrete_size
-                self._dev = DevicePlanner(want, self.vehicle)
+            else:                               # a context with this checker's mode / inflation / vehicle / rollout constants
+                self._dev = DevicePlanner(want, self.vehicle, device=getattr(base, "device", 0), max_pops=base.cfg.max_pops)
                 self._dev.load([self.map.scenario])
         return self._dev
 

@@ -1,0 +1,5 @@
+"""Shim with the reference's module path `map/costmap.py`: re-exports automatedvaletparking_b200.map.costmap
+(this directory, and only this directory, goes in front of the reference root on sys.path)."""
+from automatedvaletparking_b200.map.costmap import *  # noqa: F401,F403
+import automatedvaletparking_b200.map.costmap as _impl
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

@@ -33,8 +33,24 @@ class PathPlanner:
         else:
             self.collision_checker = collision_check.distance_checker(map=map, vehicle=vehicle, config=config)
         self._planner = None
+        self._ctx = None
         self.last_summary = None
         self.pop_indices = None
+
+    def _context(self):
+        """ONE device context for this planner's whole searches, shared with the collision checker when the derived
+        avp_config matches (same config, vehicle and max_pops) -- not one per a_star_plan call"""
+        if self._ctx is None:
+            from ..batch import DevicePlanner
+            from ..hostcfg import make_avp_config
+            chk = self.collision_checker._device()
+            want = dict(self.config)
+            want['map_discrete_size'] = self.map.discrete_size
+            if bytes(make_avp_config(want, self.vehicle, max_pops=self.max_pops)) == bytes(chk.cfg):
+                self._ctx = chk
+            else:
+                self._ctx = DevicePlanner(want, self.vehicle, device=getattr(chk, "device", 0), max_pops=self.max_pops)
+        return self._ctx
 
     @property
     def planner(self) -> hybrid_a_star:
@@ -52,13 +68,9 @@ class PathPlanner:
         return out_final_path, path_info, split_path_list
 
     def a_star_plan(self) -> Tuple[List[List], List[List], PATH]:
-        from ..batch import DevicePlanner
-        dev = DevicePlanner(self.config, self.vehicle, max_pops=self.max_pops)
-        try:
-            dev.load([self.map.scenario])
-            res = dev.plan(cap_path=4096, cap_pops=self.max_pops)
-        finally:
-            pass
+        dev = self._context()
+        dev.load([self.map.scenario])
+        res = dev.plan(cap_path=4096, cap_pops=self.max_pops)
         s = res.summaries[0]
         self.last_summary = s
         self.pop_indices = res.pop_indices(0).copy()
@@ -68,7 +80,6 @@ class PathPlanner:
                 print('current node index:', int(idx))
                 print('---------------')
         status = int(s['status'])
-        dev.close()
         if status == 1:
             raise AttributeError("'NoneType' object has no attribute 'x'")        # path_planner.py:104 on an exhausted open list
         if status == 3:

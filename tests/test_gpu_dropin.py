@@ -14,20 +14,24 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def dropin(native_built):
-    """import the drop-ins under the reference's own module names (map, collision_check, path_plan, config)"""
-    pkg = os.path.join(ROOT, "automatedvaletparking_b200")
-    sys.path.insert(0, pkg)
+    """import the drop-ins under the reference's own module names (map, collision_check, path_plan, config) with
+    INTEGRATION.md's sys.path setup: the shim directory first"""
+    shim = os.path.join(ROOT, "automatedvaletparking_b200", "dropin")
+    sys.path.insert(0, shim)
     try:
         for name in [n for n in sys.modules if n.split(".")[0] in ("map", "collision_check", "path_plan", "config")]:
             del sys.modules[name]
-        from automatedvaletparking_b200.map import costmap
-        from automatedvaletparking_b200.path_plan import path_planner, hybrid_a_star, rs_curve, compute_h
-        from automatedvaletparking_b200.collision_check import collision_check
-        from automatedvaletparking_b200.config import read_config
+        from map import costmap
+        from path_plan import path_planner, hybrid_a_star, rs_curve, compute_h
+        from collision_check import collision_check
+        from config import read_config
+        assert costmap.__file__.startswith(shim) and path_planner.__file__.startswith(shim)
         yield dict(costmap=costmap, path_planner=path_planner, hybrid_a_star=hybrid_a_star, rs_curve=rs_curve, compute_h=compute_h,
                    collision_check=collision_check, config=read_config.read_config("config"))
     finally:
-        sys.path.remove(pkg)
+        sys.path.remove(shim)
+        for name in [n for n in sys.modules if n.split(".")[0] in ("map", "collision_check", "path_plan", "config")]:
+            del sys.modules[name]
 
 
 def _case_csv(tmp_path, n):
