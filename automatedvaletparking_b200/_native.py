@@ -20,7 +20,7 @@ c_vp = ctypes.c_void_p
 
 EXPORTS = [
     "avp_create", "avp_destroy", "avp_last_error", "avp_launch_count", "avp_scenarios_upload", "avp_rasterise",
-    "avp_fetch_map", "avp_collision_check", "avp_corridor", "avp_expand_pure", "avp_rs_optimal", "avp_plan_batch",
+    "avp_fetch_map", "avp_collision_check", "avp_check_start_goal", "avp_corridor", "avp_expand_pure", "avp_rs_optimal", "avp_plan_batch",
     "avp_plan_batch_resident", "avp_fetch_results", "avp_plan_configure", "avp_result_device_buffer",
     "avp_fetch_hvalues", "avp_fetch_hq_log", "avp_device_info", "avp_set_watchdog", "avp_fetch_debug", "avp_timer_start", "avp_timer_stop", "avp_last_search_ms", "avp_last_search_passes", "avp_fetch_profile", "avp_fetch_warp_profile", "avp_dijkstra_query",
 ]
@@ -53,6 +53,7 @@ def lib():
     L.avp_rasterise.argtypes = [c_vp]
     L.avp_fetch_map.argtypes = [c_vp, ctypes.c_int, c_ip, c_dp, c_u8p, ctypes.c_int64]
     L.avp_collision_check.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, c_dp, c_u8p]
+    L.avp_check_start_goal.argtypes = [c_vp, c_u8p]
     L.avp_corridor.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_double, c_dp, c_ip]
     L.avp_expand_pure.argtypes = [c_vp, ctypes.c_int, c_dp, c_dp, c_ip, c_dp]
     L.avp_rs_optimal.argtypes = [c_vp, ctypes.c_int, c_dp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,

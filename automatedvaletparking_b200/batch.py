@@ -147,16 +147,12 @@ class DevicePlanner:
         return out, st
 
     def start_goal_collisions(self):
-        """distance_checker.check at every loaded scenario's start and goal pose (scenario recipes)."""
-        from . import hostcfg  # noqa: F401
-        a = np.zeros(self.n, dtype=bool)
-        b = np.zeros(self.n, dtype=bool)
-        P = self.batch.poses
-        for k in range(self.n):
-            # the search wraps headings with pi_2_pi (hybrid_a_star.py:105,109); check() sees the same values
-            r = self.check(k, [[P[k, 0], P[k, 1], _pi_2_pi(P[k, 2])], [P[k, 3], P[k, 4], _pi_2_pi(P[k, 5])]])
-            a[k], b[k] = r[0], r[1]
-        return a, b
+        """distance_checker.check at every loaded scenario's start and goal pose (scenario recipes); one launch for the batch.
+        The search wraps headings with pi_2_pi (hybrid_a_star.py:105,109); the check sees the same values."""
+        out = np.zeros(2 * self.n, dtype=np.uint8)
+        self._ck(self._L.avp_check_start_goal(self._h, out.ctypes.data_as(_native.c_u8p)), "avp_check_start_goal")
+        o = out.reshape(self.n, 2).astype(bool)
+        return o[:, 0].copy(), o[:, 1].copy()
 
     def expand_pure(self, s: int, parent):
         n = 2 * self.cfg.steering_angle_num

@@ -10,8 +10,7 @@
 #include <algorithm>
 #include <utility>
 #include <time.h>
-#include "avp_kernels.cuh"
-#include "avp_search_pipe.cuh"
+#include "avp_plan.cuh"
 
 struct avp_ctx {
   int device = 0;
@@ -35,22 +34,23 @@ struct avp_ctx {
   // per-id arrays
   int64_t id_count = 0;
   int32_t *d_hval = nullptr, *d_ost = nullptr; double *d_gx = nullptr, *d_gy = nullptr;
-  // per-slot workspaces
-  int ws_slots = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
-  NodeShot *d_nshot = nullptr; int nshot_slots = 0, nshot_node_cap = 0;   // pipelined pass-2 kernel only
+  // search workspaces: per scenario (Dijkstra queue, ScenState), per slot (nodes, open heap, exact-pose table), per CTA (course scratch)
+  int ws_n = 0, ws_slots = 0, ws_ctas = 0, node_cap = 0, htab_size = 0, dheap_cap = 0;
+  NodeShot *d_nshot = nullptr;
   Node *d_nodes = nullptr; OEnt *d_oheap = nullptr; int32_t *d_htab = nullptr; unsigned long long *d_dheap = nullptr;
-  int slots_wide = 0; int slots_w[3] = {0, 0, 0}; int32_t *d_worklist = nullptr; int worklist_cap = 0;
-  int32_t *d_order = nullptr;      // pass-1 processing order: expensive scenarios (far start-goal pairs) first
+  ScenState *d_state = nullptr; PlanCtl *d_ctl = nullptr; int32_t *d_queue = nullptr, *d_slot_ring = nullptr; int q_mask = 0, slot_mask = 0;
+  int32_t *d_order = nullptr;      // processing order: expensive scenarios (far start-goal pairs) first
   double *d_course = nullptr; int32_t *d_course_dir = nullptr;
+  int plan_block = 512, plan_grid = 0, ctas_per_sm[2] = {1, 2};
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
   long long *d_prof = nullptr, *d_wprof = nullptr;
   int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
-  float pass_ms[2] = {0.f, 0.f}; int n_pending = 0; int wide_block = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+  float pass_ms[2] = {0.f, 0.f}; int n_suspends = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evM = nullptr, evA = nullptr, evB = nullptr;
   // persistent single-scenario Dijkstra query state (drop-in for compute_h.Dijkstra)
-  int dq_scen = -1; unsigned long long *d_dq_save = nullptr, *d_dq_gheap = nullptr; DijPersist *d_dq_state = nullptr; int32_t *d_dq_out = nullptr;
+  int dq_scen = -1; unsigned long long *d_dq_gheap = nullptr; DijPersist *d_dq_state = nullptr; int32_t *d_dq_out = nullptr;
   // scratch for the small API kernels
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
 };
@@ -93,23 +93,15 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return -8; }
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
-  int per_sm = 0;
-  cudaFuncSetAttribute(k_search<AVP_BLOCK_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(AVP_BLOCK_NARROW));
-  cudaFuncSetAttribute(k_search<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(128));
-  cudaFuncSetAttribute(k_search<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
-  cudaFuncSetAttribute(k_search<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<AVP_BLOCK_NARROW>, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW)) != cudaSuccess || per_sm < 1) per_sm = 1;
-  { const char *ne = getenv("AVP_NARROW_PER_SM"); if (ne && atoi(ne) >= 1 && atoi(ne) < per_sm) per_sm = atoi(ne); }   // development aid: occupancy sweep of pass 1
-  ctx->slots = ctx->n_sm * per_sm;               // persistent grids: multiples of the SM count
-  int o = 0;
-  ctx->slots_w[0] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<512>, 512, 12 * avp_sm_open(512)) == cudaSuccess && o > 0) ? o : 1);
-  ctx->slots_w[1] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<256>, 256, 12 * avp_sm_open(256)) == cudaSuccess && o > 0) ? o : 1);
-  ctx->slots_w[2] = ctx->n_sm * ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<128>, 128, 12 * avp_sm_open(128)) == cudaSuccess && o > 0) ? o : 1);
-  ctx->slots_wide = ctx->slots_w[0];
-  cudaFuncSetAttribute(k_search_pipe<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
-  cudaFuncSetAttribute(k_search_pipe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
-  cudaFuncSetAttribute(k_search_pipe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(128));
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
+  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
+  {
+    int o = 0;
+    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, 12 * avp_sm_open(512)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, 12 * avp_sm_open(256)) == cudaSuccess && o > 0) ? o : 1;
+  }
+  ctx->slots = ctx->n_sm * ctx->ctas_per_sm[0];               // persistent grids: multiples of the SM count
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evM);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
   *out = ctx;
   return 0;
@@ -128,9 +120,10 @@ static void free_results(avp_ctx *ctx) {
   ctx->d_sums = nullptr; ctx->d_paths = nullptr; ctx->d_pops = nullptr; ctx->d_hq = nullptr; ctx->res_n = 0;
 }
 static void free_ws(avp_ctx *ctx) {
-  free_dev(ctx->d_nshot); ctx->d_nshot = nullptr; ctx->nshot_slots = 0; ctx->nshot_node_cap = 0;
-  free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap); free_dev(ctx->d_course); free_dev(ctx->d_course_dir);
-  ctx->d_nodes = nullptr; ctx->d_oheap = nullptr; ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_slots = 0;
+  free_dev(ctx->d_nshot); free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap);
+  free_dev(ctx->d_state); free_dev(ctx->d_ctl); free_dev(ctx->d_queue); free_dev(ctx->d_slot_ring); free_dev(ctx->d_course); free_dev(ctx->d_course_dir);
+  ctx->d_nshot = nullptr; ctx->d_nodes = nullptr; ctx->d_oheap = nullptr; ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_state = nullptr; ctx->d_ctl = nullptr;
+  ctx->d_queue = ctx->d_slot_ring = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_n = ctx->ws_slots = ctx->ws_ctas = 0;
 }
 
 extern "C" int avp_destroy(avp_ctx *ctx) {
@@ -138,10 +131,10 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
-  free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_worklist);
+  free_dev(ctx->d_counter); free_dev(ctx->d_scratch);
   free_dev(ctx->d_order);
-  free_dev(ctx->d_dq_save); free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1); if (ctx->evM) cudaEventDestroy(ctx->evM);
   if (ctx->evA) cudaEventDestroy(ctx->evA); if (ctx->evB) cudaEventDestroy(ctx->evB);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -277,6 +270,21 @@ extern "C" int avp_collision_check(avp_ctx *ctx, int s, int m, const double *pos
   return 0;
 }
 
+extern "C" int avp_check_start_goal(avp_ctx *ctx, uint8_t *out2n) {
+  if (!ctx) return -3;
+  if (ctx->n <= 0 || !out2n) FAIL("avp_check_start_goal: bad arguments");
+  if (!ctx->rasterised) FAIL("avp_check_start_goal: call avp_rasterise first");
+  CK(cudaSetDevice(ctx->device));
+  const int m = 2 * ctx->n;
+  if (ensure_scratch(ctx, (size_t)m + 64)) return -1;
+  uint8_t *d_o = (uint8_t *)ctx->d_scratch;
+  k_check_start_goal<<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->cfg, ctx->d_scen, ctx->n, ctx->d_cells, ctx->d_col, d_o); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out2n, d_o, m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 extern "C" int avp_corridor(avp_ctx *ctx, int s, int m, const double *poses, double expand_dis, double *out4, int32_t *status) {
   if (!ctx) return -3;
   if (s < 0 || s >= ctx->n || m < 0 || !poses || !out4 || !status) FAIL("avp_corridor: bad arguments");
@@ -345,24 +353,39 @@ extern "C" int avp_rs_optimal(avp_ctx *ctx, int m, const double *q, double maxc,
   return 0;
 }
 
-static int ensure_ws(avp_ctx *ctx) {
+/* Workspaces of a launch over the uploaded batch.  Slots: a search owns one from its first pop to its last (also while it
+ * waits in the run queue), so as many as there are scenarios is the comfortable number; with less memory than that the
+ * kernel sends fresh scenarios to the back of the queue while every slot is taken. */
+static int ensure_ws(avp_ctx *ctx, int ctas) {
   const int nchild = 2 * ctx->cfg.steering_angle_num;
   const int max_pops = ctx->cfg.max_pops > 0 ? ctx->cfg.max_pops : 20000;
   const int node_cap = nchild * (max_pops + 1) + 2;
-  int slots = ctx->slots; if (slots > ctx->n) slots = ctx->n;      // no more CTAs than scenarios
-  if (slots < 1) slots = 1;
-  if (ctx->ws_slots >= slots && ctx->node_cap == node_cap) return 0;
+  const int n = ctx->n;
+  if (ctx->ws_n >= n && ctx->ws_n <= 4 * n + 64 && ctx->ws_ctas >= ctas && ctx->node_cap == node_cap) return 0;      // grow-only with slack
   free_ws(ctx);
   int hb = 1; while (hb < 2 * node_cap) hb <<= 1;
   ctx->node_cap = node_cap; ctx->htab_size = hb; ctx->dheap_cap = 1 << 16;
-  const int S = slots;        // as many slots as CTAs that can be resident for this batch
-  CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)S * node_cap));
-  CK(cudaMalloc(&ctx->d_oheap, sizeof(OEnt) * (size_t)S * node_cap));
-  CK(cudaMalloc(&ctx->d_htab, sizeof(int32_t) * (size_t)S * hb));
-  CK(cudaMalloc(&ctx->d_dheap, sizeof(unsigned long long) * (size_t)S * ctx->dheap_cap));
-  CK(cudaMalloc(&ctx->d_course, sizeof(double) * (size_t)S * 3 * AVP_COURSE_CAP));
-  CK(cudaMalloc(&ctx->d_course_dir, sizeof(int32_t) * (size_t)S * AVP_COURSE_CAP));
-  ctx->ws_slots = S;
+  CK(cudaMalloc(&ctx->d_dheap, sizeof(unsigned long long) * (size_t)n * ctx->dheap_cap));
+  CK(cudaMalloc(&ctx->d_state, sizeof(ScenState) * (size_t)n));
+  CK(cudaMalloc(&ctx->d_ctl, sizeof(PlanCtl)));
+  int ring = 2; while (ring < n + 1) ring <<= 1;
+  CK(cudaMalloc(&ctx->d_queue, sizeof(int32_t) * ring)); ctx->q_mask = ring - 1;
+  CK(cudaMalloc(&ctx->d_course, sizeof(double) * (size_t)ctas * 3 * AVP_COURSE_CAP));
+  CK(cudaMalloc(&ctx->d_course_dir, sizeof(int32_t) * (size_t)ctas * AVP_COURSE_CAP));
+  const size_t slot_bytes = (sizeof(Node) + sizeof(NodeShot) + sizeof(OEnt)) * (size_t)node_cap + sizeof(int32_t) * (size_t)hb;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  size_t fit = (size_t)((double)free_b * 0.8) / slot_bytes;
+  { const char *se = getenv("AVP_SLOTS"); if (se && atoi(se) > 0) fit = (size_t)atoi(se); }      // development aid: force the slot pool to run dry
+  int slots = n; if ((size_t)slots > fit) slots = (int)fit;
+  if (slots < ctas + 1 && slots < n) FAIL("plan: not enough device memory for the search workspaces");
+  CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)slots * node_cap));
+  CK(cudaMalloc(&ctx->d_nshot, sizeof(NodeShot) * (size_t)slots * node_cap));
+  CK(cudaMalloc(&ctx->d_oheap, sizeof(OEnt) * (size_t)slots * node_cap));
+  CK(cudaMalloc(&ctx->d_htab, sizeof(int32_t) * (size_t)slots * hb));
+  int sring = 2; while (sring < slots + 1) sring <<= 1;
+  CK(cudaMalloc(&ctx->d_slot_ring, sizeof(int32_t) * sring)); ctx->slot_mask = sring - 1;
+  ctx->ws_n = n; ctx->ws_slots = slots; ctx->ws_ctas = ctas;
   return 0;
 }
 
@@ -410,99 +433,67 @@ static int wait_search(avp_ctx *ctx, cudaEvent_t ev) {
   return 0;
 }
 
-/* Two passes.  Pass 1: every scenario on narrow CTAs (many concurrent scenarios: the eager
- * Dijkstra and short searches dominate) with a pop budget.  Pass 2: the scenarios that ran out of
- * budget are re-planned from scratch on wide CTAs, where the per-pop latency is ~BLOCK-parallel.
- * Results are identical to a single pass (a search is a deterministic function of its scenario). */
+/* One pass: queue / slot pool initialisation, the eager Dijkstra of every scenario (one warp each), then ONE persistent search
+ * kernel (avp_plan.cuh).  No host round trip in between; results are a deterministic function of the scenarios whatever the
+ * scheduling (quantum, CTA width, SM-pair placement). */
 static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   if (ctx->n <= 0) FAIL("plan: no scenarios uploaded");
   ctx->dq_scen = -1;
   if (!ctx->rasterised) FAIL("plan: call avp_rasterise first");
   CK(cudaSetDevice(ctx->device));
-  if (ensure_ws(ctx)) return -1;
-  KParams P; memset(&P, 0, sizeof(P));
+  // CTA width: 512 threads, one CTA per SM (15 evaluator warps per pop: the shortest pop), or 256 threads, two CTAs per SM
+  // (more searches in flight per SM: throughput for batches with far more long searches than SMs)
+  int block = 512;
+  { const char *be = getenv("AVP_PLAN_BLOCK"); if (be && atoi(be) == 256) block = 256; }
+  const int per_sm = ctx->ctas_per_sm[block == 512 ? 0 : 1];
+  int grid = ctx->n_sm * per_sm; if (grid > ctx->n) grid = ctx->n;
+  if (ensure_ws(ctx, ctx->n_sm * ctx->ctas_per_sm[1] > grid ? ctx->n_sm * ctx->ctas_per_sm[1] : grid)) return -1;
+  PlanParams PP; memset(&PP, 0, sizeof(PP));
+  KParams &P = PP.K;
   P.cfg = ctx->cfg; if (P.cfg.max_pops <= 0) P.cfg.max_pops = 20000;
   P.n_scen = ctx->n; P.scen = ctx->d_scen; P.cost = ctx->d_cost; P.cells = ctx->d_cells; P.col_start = ctx->d_col;
   P.hval = ctx->d_hval; P.ost = ctx->d_ost; P.gx = ctx->d_gx; P.gy = ctx->d_gy;
-  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap;
+  P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.nshot = ctx->d_nshot;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.htab_stride = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
-  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = ctx->d_dbg; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof; { const char *tpp = getenv("AVP_TRACE_POP"); P.trace_pop = tpp ? atoi(tpp) : -1; } P.watchdog_cycles = ctx->watchdog_cycles;
-  const char *pb = getenv("AVP_POP_BUDGET");
-  const int budget = pb ? atoi(pb) : 1024;
-  P.work_list = ctx->d_order; P.n_work = ctx->n; P.pop_budget = (budget > 0 && budget < P.cfg.max_pops) ? budget : P.cfg.max_pops;
-  {   // pass 1 creates at most nchild * (pop_budget + 1) nodes per scenario: a table of that size is cleared and probed, not the full one
-    const long long need = 2ll * (2 * P.cfg.steering_angle_num) * ((long long)P.pop_budget + 2);
-    int hb = 1024; while (hb < need && hb < ctx->htab_size) hb <<= 1;
-    if (hb < ctx->htab_size) P.htab_size = hb;
-  }
-  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  int grid = ctx->slots; if (grid > ctx->n) grid = ctx->n;
+  P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = getenv("AVP_HOST_TIMEOUT_S") ? ctx->d_dbg : nullptr; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof;
+  { const char *tpp = getenv("AVP_TRACE_POP"); P.trace_pop = tpp ? atoi(tpp) : -1; } P.watchdog_cycles = ctx->watchdog_cycles;
+  P.work_list = ctx->d_order; P.n_work = ctx->n;
+  PP.state = ctx->d_state; PP.ctl = ctx->d_ctl; PP.queue = ctx->d_queue; PP.q_mask = ctx->q_mask;
+  PP.slot_ring = ctx->d_slot_ring; PP.slot_mask = ctx->slot_mask; PP.n_slots = ctx->ws_slots;
+  { const char *qe = getenv("AVP_QUANTUM"); PP.quantum = (qe && atoi(qe) > 0) ? atoi(qe) : 512; }
+  // SM pairs: only when the grid covers every SM (else the hardware's placement decides) and not switched off (AVP_SPREAD=0)
+  { const char *se = getenv("AVP_SPREAD"); P.spread = (grid == ctx->n_sm * per_sm && ctx->n_sm >= 4 && !(se && atoi(se) == 0)) ? 1 : 0; }
+  { const char *me = getenv("AVP_SPREAD_MAX"); PP.spread_max = me ? atoi(me) : (ctx->n_sm / 2 + ctx->n_sm / 4) * per_sm; }
+#ifdef AVP_PROFILE
+  CK(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * (size_t)ctx->n * 16, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_wprof, 0, sizeof(long long) * (size_t)ctx->n * 384, ctx->stream));
+#endif
+  const int ring_max = (ctx->q_mask > ctx->slot_mask ? ctx->q_mask : ctx->slot_mask) + 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_search<AVP_BLOCK_NARROW><<<grid, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW), ctx->stream>>>(P); ctx->launches++;
+  k_plan_init<<<(ring_max + 255) / 256, 256, 0, ctx->stream>>>(PP); ctx->launches++;
+  {
+    int dgrid = (ctx->n + AVP_DIJ_WARPS - 1) / AVP_DIJ_WARPS; const int dmax = ctx->n_sm * 5; if (dgrid > dmax) dgrid = dmax;
+    k_dij_eager<<<dgrid, AVP_DIJ_WARPS * 32, 0, ctx->stream>>>(PP); ctx->launches++;
+  }
+  CK(cudaEventRecord(ctx->evM, ctx->stream));
+  if (block == 512) k_plan<512><<<grid, 512, 12 * avp_sm_open(512), ctx->stream>>>(PP);
+  else k_plan<256><<<grid, 256, 12 * avp_sm_open(256), ctx->stream>>>(PP);
+  ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());
+  ctx->plan_block = block; ctx->plan_grid = grid;
   if (wait_search(ctx, ctx->ev1)) return -1;
   float ms1 = 0.f, ms2 = 0.f;
-  CK(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1));
-  ctx->pass_ms[0] = ms1; ctx->pass_ms[1] = 0.f; ctx->n_pending = 0;
-  if (P.pop_budget < P.cfg.max_pops) {
-    std::vector<avp_plan_summary> hs(ctx->n);
-    CK(cudaMemcpyAsync(hs.data(), ctx->d_sums, sizeof(avp_plan_summary) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<int32_t> list;
-    for (int i = 0; i < ctx->n; ++i) if (hs[i].status == AVP_PENDING) list.push_back(i);
-    ctx->n_pending = (int)list.size();
-    if (!list.empty()) {
-      if ((int)list.size() > ctx->worklist_cap) { free_dev(ctx->d_worklist); ctx->d_worklist = nullptr; CK(cudaMalloc(&ctx->d_worklist, sizeof(int32_t) * list.size())); ctx->worklist_cap = (int)list.size(); }
-      CK(cudaMemcpyAsync(ctx->d_worklist, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-      P.work_list = ctx->d_worklist; P.n_work = (int)list.size(); P.pop_budget = P.cfg.max_pops; P.htab_size = ctx->htab_size;
-      // widest CTA whose persistent grid still holds every pending scenario at once (one wave)
-      const int npend = (int)list.size();
-      int which = 3;
-      for (int w = 0; w < 3; ++w) if (npend <= ctx->slots_w[w] && npend <= ctx->ws_slots) { which = w; break; }
-      const char *fw = getenv("AVP_WIDE_BLOCK");
-      if (fw) { const int b = atoi(fw); which = b == 512 ? 0 : b == 256 ? 1 : b == 128 ? 2 : 3; }
-      int cap = which < 3 ? ctx->slots_w[which] : ctx->slots;
-      int grid2 = cap; if (grid2 > npend) grid2 = npend; if (grid2 > ctx->ws_slots) grid2 = ctx->ws_slots;
-      ctx->wide_block = which == 0 ? 512 : which == 1 ? 256 : which == 2 ? 128 : AVP_BLOCK_NARROW;
-      // pass 2 runs the pipelined kernel (avp_search_pipe.cuh); AVP_PIPE=0 selects the phase-sequential k_search (A/B runs)
-      const char *pe = getenv("AVP_PIPE");
-      const bool pipe = which < 3 && !(pe && atoi(pe) == 0);
-      // the widest pipelined kernel is launched on every SM and one SM of each pair (TPC) takes the work (avp_search_pipe.cuh);
-      // AVP_SPREAD=0: one CTA per pending scenario, placed by the hardware (A/B runs)
-      const char *se = getenv("AVP_SPREAD");
-      // only while the pending scenarios (nearly) fit one per SM pair: two busy SMs of a pair are slower each but faster together
-      // (break-even near 1.5 scenarios per pair on the bench recipe: measured at 90 pending, modelled from the pop counts of other seeds)
-      const bool spread = pipe && which == 0 && !(se && atoi(se) == 0) && ctx->ws_slots >= ctx->n_sm && ctx->n_sm >= 4 &&
-                          npend <= (getenv("AVP_SPREAD_MAX") ? atoi(getenv("AVP_SPREAD_MAX")) : ctx->n_sm / 2 + ctx->n_sm / 4);
-      P.spread = spread ? 1 : 0;
-      if (spread) grid2 = ctx->n_sm;
-      if (pipe && (ctx->nshot_slots < grid2 || ctx->nshot_node_cap != ctx->node_cap)) {
-        free_dev(ctx->d_nshot); ctx->d_nshot = nullptr; ctx->nshot_slots = 0;
-        const int ns = std::max(grid2, std::min(ctx->ws_slots, ctx->slots_w[0]));
-        CK(cudaMalloc(&ctx->d_nshot, sizeof(NodeShot) * (size_t)ns * ctx->node_cap));
-        ctx->nshot_slots = ns; ctx->nshot_node_cap = ctx->node_cap;
-      }
-      P.nshot = ctx->d_nshot;
-      CK(cudaEventRecord(ctx->ev0, ctx->stream));
-      if (pipe && which == 0) k_search_pipe<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
-      else if (pipe && which == 1) k_search_pipe<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
-      else if (pipe && which == 2) k_search_pipe<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
-      else if (which == 0) k_search<512><<<grid2, 512, 12 * avp_sm_open(512), ctx->stream>>>(P);
-      else if (which == 1) k_search<256><<<grid2, 256, 12 * avp_sm_open(256), ctx->stream>>>(P);
-      else if (which == 2) k_search<128><<<grid2, 128, 12 * avp_sm_open(128), ctx->stream>>>(P);
-      else k_search<AVP_BLOCK_NARROW><<<grid2, AVP_BLOCK_NARROW, 12 * avp_sm_open(AVP_BLOCK_NARROW), ctx->stream>>>(P);
-      ctx->launches++;
-      CK(cudaEventRecord(ctx->ev1, ctx->stream));
-      CK(cudaGetLastError());
-      if (wait_search(ctx, ctx->ev1)) return -1;
-      CK(cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev1));
-      ctx->pass_ms[1] = ms2;
-    }
-  }
+  CK(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->evM));
+  CK(cudaEventElapsedTime(&ms2, ctx->evM, ctx->ev1));
+  ctx->pass_ms[0] = ms1; ctx->pass_ms[1] = ms2;
   if (elapsed_ms) *elapsed_ms = ms1 + ms2;
+  PlanCtl c;
+  CK(cudaMemcpyAsync(&c, ctx->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n_suspends = c.n_suspends;
+  if (c.finalised != ctx->n || c.error) { char b[160]; snprintf(b, sizeof b, "plan: the search kernel ended with %d of %d scenarios finished (queue error %d)", c.finalised, ctx->n, c.error); ctx->err = b; return -12; }
   return 0;
 }
 
@@ -575,7 +566,7 @@ extern "C" int avp_fetch_hq_log(avp_ctx *ctx, int s, int32_t *log3, int cap_entr
 
 extern "C" int avp_device_info(avp_ctx *ctx, int32_t *n_sm, int32_t *slots, int32_t *block) {
   if (!ctx) return -3;
-  if (n_sm) *n_sm = ctx->n_sm; if (slots) *slots = ctx->slots; if (block) *block = AVP_BLOCK_NARROW;
+  if (n_sm) *n_sm = ctx->n_sm; if (slots) *slots = ctx->slots; if (block) *block = ctx->plan_block;
   return 0;
 }
 
@@ -614,10 +605,12 @@ extern "C" int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms) {
   if (elapsed_ms) *elapsed_ms = ctx->pass_ms[0] + ctx->pass_ms[1];
   return 0;
 }
-/* per-pass CUDA-event times of the last search and the number of scenarios handed to pass 2 */
-extern "C" int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_pass2, int32_t *n_pass2) {
+/* CUDA-event times of the last search: eager Dijkstra kernel, search kernel; n_info = number of times a search let go of its SM
+ * (round-robin suspensions) + 100000 * CTA width */
+extern "C" int avp_last_search_passes(avp_ctx *ctx, float *ms_dijkstra, float *ms_search, int32_t *n_info) {
   if (!ctx) return -3;
-  if (ms_pass1) *ms_pass1 = ctx->pass_ms[0]; if (ms_pass2) *ms_pass2 = ctx->pass_ms[1]; if (n_pass2) *n_pass2 = ctx->n_pending + 100000 * ctx->wide_block;
+  if (ms_dijkstra) *ms_dijkstra = ctx->pass_ms[0]; if (ms_search) *ms_search = ctx->pass_ms[1];
+  if (n_info) *n_info = (ctx->n_suspends % 100000) + 100000 * ctx->plan_block;
   return 0;
 }
 
@@ -653,15 +646,14 @@ extern "C" int avp_dijkstra_query(avp_ctx *ctx, int s, int reset, double node_x,
   if (!ctx->rasterised) FAIL("avp_dijkstra_query: call avp_rasterise first");
   CK(cudaSetDevice(ctx->device));
   const int gcap = 1 << 20;
-  if (!ctx->d_dq_save) {
-    CK(cudaMalloc(&ctx->d_dq_save, sizeof(unsigned long long) * AVP_SM_HEAP));
+  if (!ctx->d_dq_gheap) {
     CK(cudaMalloc(&ctx->d_dq_gheap, sizeof(unsigned long long) * gcap));
     CK(cudaMalloc(&ctx->d_dq_state, sizeof(DijPersist)));
     CK(cudaMalloc(&ctx->d_dq_out, sizeof(int32_t) * 4));
     CK(cudaMemset(ctx->d_dq_state, 0, sizeof(DijPersist)));
   }
   if (ctx->dq_scen != s) { reset = 1; ctx->dq_scen = s; }
-  k_dij_query<<<1, 32, 0, ctx->stream>>>(ctx->d_scen, s, ctx->d_cost, ctx->d_hval, ctx->d_ost, ctx->d_gx, ctx->d_gy, ctx->d_dq_save, ctx->d_dq_gheap, gcap,
+  k_dij_query<<<1, 32, 0, ctx->stream>>>(ctx->d_scen, s, ctx->d_cost, ctx->d_hval, ctx->d_ost, ctx->d_gx, ctx->d_gy, ctx->d_dq_gheap, gcap,
                                          ctx->d_dq_state, reset, node_x, node_y, ctx->d_dq_out);
   ctx->launches++;
   CK(cudaGetLastError());

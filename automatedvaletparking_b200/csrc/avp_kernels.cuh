@@ -5,17 +5,10 @@
 //   k_check_batch                          : distance_checker / two_circle_checker .check
 //   k_expand_pure                          : pure part of hybrid_a_star.expand_node + rs length
 //   k_rs_optimal                           : rs_curve.calc_optimal_path
-//   k_search                               : PathPlanner.a_star_plan, whole search per scenario
-//                                            (persistent CTAs pulling scenarios from an atomic counter)
+// plus the containers (heapq emulations, exact-pose table) and the Dijkstra of the search kernels in avp_plan.cuh.
 #pragma once
 #include "avp_dev.cuh"
 
-#ifndef AVP_BLOCK_NARROW
-#define AVP_BLOCK_NARROW 64   // pass 1: many narrow CTAs (Dijkstra-bound, short searches)
-#endif
-#ifndef AVP_BLOCK_WIDE
-#define AVP_BLOCK_WIDE 512    // pass 2: few wide CTAs for the long tail (per-pop latency bound)
-#endif
 #ifndef AVP_SM_HEAP
 #define AVP_SM_HEAP 1024      // Dijkstra heap entries kept in shared memory (the rest spills to L2/HBM)
 #endif
@@ -53,14 +46,14 @@ struct KParams {
   int32_t *hval;   // distance of the first closedlist entry with this grid id, -1 = none
   int32_t *ost;    // -1 unseen, -2 popped, >= 0 current distance while in the open heap
   double *gx, *gy; // lattice coordinates of the Grid object holding this id
-  // per-slot (persistent CTA) workspaces
-  unsigned long long *dheap; int dheap_cap;
+  unsigned long long *dheap; int dheap_cap;   // Dijkstra queue, dheap_cap entries per SCENARIO
+  // per-slot workspaces (a slot belongs to one search from its first pop to its last)
   Node *nodes; int node_cap;
-  NodeShot *nshot;                // node_cap per slot (pipelined kernel only)
-  struct OEnt *oheap;             // open heap entries beyond the shared-memory part (node_cap per slot)
-  int32_t *htab; int htab_size;   // power of two: entries used by this launch (pass 1 needs far fewer nodes than max_pops allows)
+  NodeShot *nshot;                // node_cap per slot
+  struct OEnt *oheap;             // open heap (node_cap entries per slot; [0, SMO) = save area of the shared-memory head)
+  int32_t *htab; int htab_size;   // power of two
   int htab_stride;                // entries between two slots' tables
-  double *course;                 // 3*AVP_COURSE_CAP doubles per slot
+  double *course;                 // 3*AVP_COURSE_CAP doubles per CTA (scratch)
   int32_t *course_dir;
   // results per scenario
   avp_plan_summary *sums;
@@ -68,12 +61,11 @@ struct KParams {
   int32_t *pops; int cap_pops;
   int32_t *hq_log;                // n * AVP_HQ_CAP * 3, may be NULL
   int *work_counter;
-  const int32_t *work_list;       // NULL: scenarios 0..n_work-1; else the ids to process (pass 2)
+  const int32_t *work_list;       // processing order (longest start-goal distance first); NULL: 0..n_work-1
   int n_work;
-  int pop_budget;                 // pass 1: a scenario still searching after this many pops ends AVP_PENDING
   long long *prof;                // n * 16 SM-cycle accumulators / counters per scenario (thread 0): phases of the main loop, may be NULL
   int trace_pop;                  // pipelined kernel: the pop whose per-warp timeline is recorded in wprof (development aid)
-  int spread;                     // pipelined kernel: the grid covers every SM and the odd SM of each pair takes work only after the even ones (see avp_api.cu)
+  int spread;                     // the grid covers every SM and the CTAs on odd SM ids stand back while few scenarios are live (avp_plan.cuh)
   long long *wprof;               // n * 16 * 24: per warp (16) and phase (8) work cycles of the pipelined kernel, may be NULL
   int *dbg;                       // n * 8 ints of progress checkpoints (development aid), may be NULL
   long long watchdog_cycles;      // 0 = off; a scenario running longer aborts with AVP_CAPACITY
@@ -200,6 +192,17 @@ __global__ void __launch_bounds__(128) k_check_batch(avp_config cfg, const ScenD
   if (w >= m) return;
   const ScenDev &S = scen[s];
   const bool hit = check_pose_warp(cfg, S, cells + S.cell_off, col_start + S.col_off, poses[3 * w], poses[3 * w + 1], poses[3 * w + 2]);
+  if ((threadIdx.x & 31) == 0) out[w] = hit ? 1 : 0;
+}
+
+// the same check for every loaded scenario's own start and goal pose (headings wrapped by pi_2_pi as the search does,
+// hybrid_a_star.py:105,109): one warp per (scenario, start | goal); out[2*s + which]
+__global__ void __launch_bounds__(128) k_check_start_goal(avp_config cfg, const ScenDev *scen, int n, const double2 *cells, const int32_t *col_start, uint8_t *out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= 2 * n) return;
+  const ScenDev &S = scen[w >> 1];
+  const double *p = S.pose + 3 * (w & 1);
+  const bool hit = check_pose_warp(cfg, S, cells + S.cell_off, col_start + S.col_off, p[0], p[1], pi_2_pi(p[2]));
   if ((threadIdx.x & 31) == 0) out[w] = hit ? 1 : 0;
 }
 
@@ -344,7 +347,9 @@ __global__ void __launch_bounds__(128) k_rs_optimal(int m, const double *q, doub
 // ------------------------------------------------------------------------------------------
 // Dijkstra (path_plan/compute_h.py), verbatim CPython heapq emulation, run by ONE warp.
 // Heap entries are 64-bit keys (distance << 32 | grid_id): Grid.__lt__ (compute_h.py:33-38)
-// is an unsigned 64-bit compare.  The first AVP_SM_HEAP entries live in shared memory.
+// is an unsigned 64-bit compare.  The heap is the array gheap[0 .. gcap) in global memory; while a kernel works
+// on it the first AVP_SM_HEAP entries live in shared memory (sheap) and gheap[0 .. AVP_SM_HEAP) is their save area
+// (dij_heap_load / dij_heap_store), so a search can be suspended on one SM and resumed on another.
 
 struct DijCtx {
   const ScenDev *S; const uint8_t *cost;
@@ -387,8 +392,8 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
   int hn = D.hn, closed_len = D.closed_len, status = 0;
   const double inv_dx = 1.0 / dx, inv_dy = 1.0 / dy;
 
-#define HP_GET(i) ((i) < AVP_SM_HEAP ? sheap[(i)] : gheap[(i) - AVP_SM_HEAP])
-#define HP_SET(i, v) do { if ((i) < AVP_SM_HEAP) sheap[(i)] = (v); else gheap[(i) - AVP_SM_HEAP] = (v); } while (0)
+#define HP_GET(i) ((i) < AVP_SM_HEAP ? sheap[(i)] : gheap[(i)])
+#define HP_SET(i, v) do { if ((i) < AVP_SM_HEAP) sheap[(i)] = (v); else gheap[(i)] = (v); } while (0)
 
   const long long term = map_index(S, node_x, node_y);
   if (term_out) *term_out = term;
@@ -440,7 +445,7 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
       const unsigned long long key_k = shfl_u64(key, k);
       if ((pm >> k) & 1u) {                   // heappush
         if (lane == 0) {
-          if (hn >= AVP_SM_HEAP + gcap) status = AVP_CAPACITY;
+          if (hn >= gcap) status = AVP_CAPACITY;
           else {
             int pos = hn++;
             while (pos > 0) {                 // heapq._siftdown
@@ -515,7 +520,7 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
 struct DijPersist { int hn, closed_len, status, inited; };
 
 __global__ void __launch_bounds__(32) k_dij_query(const ScenDev *scen, int s, const uint8_t *cost, int32_t *hval, int32_t *ost, double *gx, double *gy,
-                                                  unsigned long long *save, unsigned long long *gheap, int gcap, DijPersist *st,
+                                                  unsigned long long *gheap, int gcap, DijPersist *st,
                                                   int reset, double x, double y, int32_t *out3) {
   __shared__ unsigned long long s_heap[AVP_SM_HEAP];
   __shared__ DijCtx D;
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(32) k_dij_query(const ScenDev *scen, int s, co
     __syncwarp();
   }
   const int hn0 = st->hn;
-  for (int i = lane; i < hn0 && i < AVP_SM_HEAP; i += 32) s_heap[i] = save[i];
+  for (int i = lane; i < hn0 && i < AVP_SM_HEAP; i += 32) s_heap[i] = gheap[i];
   if (lane == 0) {
     D.S = &S; D.cost = cost + S.cost_off; D.hval = hval + S.id_off; D.ost = ost + S.id_off; D.gx = gx + S.id_off; D.gy = gy + S.id_off;
     D.sheap = s_heap; D.gheap = gheap; D.gcap = gcap; D.hn = hn0; D.closed_len = st->closed_len; D.status = 0;
@@ -537,14 +542,14 @@ __global__ void __launch_bounds__(32) k_dij_query(const ScenDev *scen, int s, co
   const int d = dij_compute_path(D, s_heap, x, y, &term);
   __syncwarp();
   const int hn1 = D.hn;
-  for (int i = lane; i < hn1 && i < AVP_SM_HEAP; i += 32) save[i] = s_heap[i];
+  for (int i = lane; i < hn1 && i < AVP_SM_HEAP; i += 32) gheap[i] = s_heap[i];
   if (lane == 0) { st->hn = hn1; st->closed_len = D.closed_len; st->status = D.status; out3[0] = d; out3[1] = D.closed_len; out3[2] = (int)term; out3[3] = D.status; }
 }
 
 // ------------------------------------------------------------------------------------------
 // hybrid A* containers (per slot)
 
-#define AVP_PENDING 7   // internal: pass 1 ran out of its pop budget; pass 2 re-plans the scenario
+#define AVP_PENDING 7   // internal: the search let go of its SM at the end of a quantum (k_plan) and waits in the run queue
 
 __device__ __forceinline__ unsigned long long pose_hash(double x, double y, double t) {
   const unsigned long long a = (unsigned long long)__double_as_longlong(x + 0.0), b = (unsigned long long)__double_as_longlong(y + 0.0),
@@ -586,17 +591,18 @@ __device__ __forceinline__ void htab_insert(int32_t *htab, int mask, const Node 
 
 // open_list: CPython heapq of Node objects ordered by Node.__lt__ (f only, hybrid_a_star.py:61-68).
 // Entries carry a copy of f (kept in sync on the reference's in-place updates through Node.hpos);
-// the first SMO entries live in shared memory (separate key / index arrays), the rest in global memory as
-// 16-byte records read with ONE load per entry: a level of a sift costs one memory round trip, not two.
+// the heap is the array ge[0 .. node_cap) of 16-byte records in global memory (ONE load per entry: a level of a sift costs one
+// memory round trip, not two); while a kernel works on it the first SMO entries live in shared memory (separate key / index
+// arrays) and ge[0 .. SMO) is their save area, so a search can be suspended on one SM and resumed on another.
 // The functions are force-inlined and take the __shared__ arrays themselves so that the compiler keeps the
 // shared address space.
 struct __align__(16) OEnt { double f; int32_t idx; int32_t pad; };
 template <int SMO>
 __device__ __forceinline__ void oh_get(const double *sf, const int32_t *si, const OEnt *ge, int i, double &f, int &idx) {
   if (i < SMO) { f = sf[i]; idx = si[i]; }
-  else { const int4 v = *reinterpret_cast<const int4 *>(&ge[i - SMO]); f = __hiloint2double(v.y, v.x); idx = v.z; }
+  else { const int4 v = *reinterpret_cast<const int4 *>(&ge[i]); f = __hiloint2double(v.y, v.x); idx = v.z; }
 }
-#define OH_SET(i, f_, idx_) do { if ((i) < SMO) { sf[(i)] = (f_); si[(i)] = (idx_); } else { int4 v_; v_.x = __double2loint(f_); v_.y = __double2hiint(f_); v_.z = (idx_); v_.w = 0; *reinterpret_cast<int4 *>(&ge[(i) - SMO]) = v_; } nodes[(idx_)].hpos = (i); } while (0)
+#define OH_SET(i, f_, idx_) do { if ((i) < SMO) { sf[(i)] = (f_); si[(i)] = (idx_); } else { int4 v_; v_.x = __double2loint(f_); v_.y = __double2hiint(f_); v_.z = (idx_); v_.w = 0; *reinterpret_cast<int4 *>(&ge[(i)]) = v_; } nodes[(idx_)].hpos = (i); } while (0)
 template <int SMO>
 __device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, OEnt *ge, Node *nodes, int pos, double fi, int item) {   // heapq._siftdown(heap, 0, pos)
   while (pos > 0) {
@@ -629,7 +635,7 @@ __device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, OEnt *ge, No
 }
 // in-place key update of an entry (hybrid_a_star.py:224-230: no re-heapify)
 template <int SMO>
-__device__ __forceinline__ void oh_set_key(double *sf, OEnt *ge, int hpos, double f) { if (hpos < SMO) sf[hpos] = f; else ge[hpos - SMO].f = f; }
+__device__ __forceinline__ void oh_set_key(double *sf, OEnt *ge, int hpos, double f) { if (hpos < SMO) sf[hpos] = f; else ge[hpos].f = f; }
 
 // hybrid_a_star.py:243-259
 __device__ __forceinline__ double node_cost(const avp_config &c, bool gear, double theta, double father_theta, bool father_gear) {
@@ -649,445 +655,7 @@ __device__ __forceinline__ void child_pose(const avp_config &cfg, const Node &cn
 }
 
 // ------------------------------------------------------------------------------------------
-// the search kernel: PathPlanner.a_star_plan (path_planner.py:58-110), one scenario per CTA at a
-// time; CTAs are persistent and pull scenarios from an atomic counter.
-
 enum { CTL_RUN = 0, CTL_EXIT = 1 };
 
 // shared-memory entries of the open heap per CTA width (dynamic shared memory: 12 bytes per entry)
 __host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? 2048 : 1024; }   // more shared memory here costs L1 hit rate (libm tables, nodes)
-
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : BLOCK == 256 ? 2 : 4)) k_search(KParams P) {
-  constexpr int NWARPS = BLOCK / 32;
-  constexpr int SMO = avp_sm_open(BLOCK);
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  double *s_of = reinterpret_cast<double *>(s_dyn);
-  int32_t *s_oi = reinterpret_cast<int32_t *>(s_dyn + sizeof(double) * SMO);
-  constexpr int CW0 = (NWARPS >= 8) ? 4 : (NWARPS / 2);        // warps [CW0, NWARPS): collision checks; [0, CW0): word selection
-  __shared__ unsigned long long s_heap[AVP_SM_HEAP];
-  __shared__ RsCand s_cand[AVP_NCHILD_MAX + 1][RS_NINST];
-  __shared__ unsigned long long s_valid[AVP_NCHILD_MAX + 1];
-  __shared__ double s_cpose[AVP_NCHILD_MAX][3];
-  __shared__ double s_rsL[AVP_NCHILD_MAX];
-  __shared__ double s_org[AVP_MAX_RS_SEG + 1][3];
-  __shared__ RsQuery s_Q[AVP_NCHILD_MAX + 1];
-  __shared__ double s_sub[AVP_NCHILD_MAX][4][4];          // sub-step poses of the successors: x, y, cos, sin (hybrid_a_star.py:185-194)
-  __shared__ RsGroupBest s_grp[AVP_NCHILD_MAX + 1][RS_NGROUP];
-  __shared__ double s_g[AVP_NCHILD_MAX], s_oldf[AVP_NCHILD_MAX], s_h1[AVP_NCHILD_MAX];
-  __shared__ int s_found[AVP_NCHILD_MAX], s_coll[AVP_NCHILD_MAX], s_need[AVP_NCHILD_MAX], s_rsok[AVP_NCHILD_MAX], s_skip[AVP_NCHILD_MAX], s_hv[AVP_NCHILD_MAX];
-  __shared__ int s_scen, s_ctl, s_cur, s_in_radius, s_npts, s_nplan, s_shot_coll, s_shot_bad;
-  __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls;
-  __shared__ RsBest s_best;
-  __shared__ DijCtx s_D;
-  __shared__ int s_on;                     // len(open_list.queue)
-
-  const avp_config &cfg = P.cfg;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = blockIdx.x;
-  const int nchild = 2 * cfg.steering_angle_num;
-  const double maxc = 1 / cfg.min_radius_turn;
-  Node *nodes = P.nodes + (size_t)slot * P.node_cap;
-  int32_t *htab = P.htab + (size_t)slot * P.htab_stride;
-  OEnt *oge = P.oheap + (size_t)slot * P.node_cap;
-  const int hmask = P.htab_size - 1;
-  double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
-  int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
-
-  for (;;) {
-    if (tid == 0) s_scen = atomicAdd(P.work_counter, 1);
-    __syncthreads();
-    if (s_scen >= P.n_work) break;
-    const int sc = P.work_list ? P.work_list[s_scen] : s_scen;
-    const ScenDev &S = P.scen[sc];
-    const double2 *cells = P.cells + S.cell_off;
-    const int32_t *col_start = P.col_start + S.col_off;
-    int32_t *hval = P.hval + S.id_off, *ost = P.ost + S.id_off;
-    const double goal[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
-    int32_t *pops = P.pops ? P.pops + (size_t)sc * P.cap_pops : nullptr;
-    int32_t *hql = P.hq_log ? P.hq_log + (size_t)sc * AVP_HQ_CAP * 3 : nullptr;
-    int *dbg = P.dbg ? P.dbg + (size_t)sc * 8 : nullptr;
-    const long long t_start = clock64();
-    long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
-#define AVP_TICK(k) do { if (tid == 0) { const long long t_ = clock64(); pc[k] += t_ - tp; tp = t_; } } while (0)
-
-    // ---- per-scenario initialisation (all threads)
-    for (int i = tid; i < S.n_ids; i += BLOCK) { hval[i] = -1; ost[i] = -1; }
-    for (int i = tid; i < P.htab_size; i += BLOCK) htab[i] = -1;
-    if (tid == 0) {
-      s_D.S = &S; s_D.cost = P.cost + S.cost_off; s_D.hval = hval; s_D.ost = ost;
-      s_D.gx = P.gx + S.id_off; s_D.gy = P.gy + S.id_off;
-      s_D.sheap = s_heap; s_D.gheap = P.dheap + (size_t)slot * P.dheap_cap; s_D.gcap = P.dheap_cap;
-      s_D.hn = 0; s_D.closed_len = 0; s_D.status = 0;
-      s_on = 0;
-      s_G = 0; s_nclosed = 0; s_npops = 0; s_nhq = 0; s_nhcalls = 0;
-      s_status = S.raster_error ? AVP_RASTER_AMBIGUOUS : 0;
-      s_cur = -1; s_in_radius = 0; s_shot_coll = 0; s_npts = 0; s_best.ok = 0;
-      if (dbg) { dbg[0] = 1; dbg[1] = 0; }
-    }
-    __syncthreads();
-
-    // ---- hybrid_a_star.__init__: eager Dijkstra to the start cell (hybrid_a_star.py:89-91), root node (:102-112)
-    if (warp == 0 && s_status == 0) {
-      long long term;
-      const int d = dij_compute_path(s_D, s_heap, S.pose[0], S.pose[1], &term);
-      if (lane == 0) {
-        if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
-        s_nhq++;
-        if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;     // the reference never returns from this compute_path: no root node
-        else {
-        Node r; r.x = S.pose[0]; r.y = S.pose[1]; r.theta = pi_2_pi(S.pose[2]); r.f = 0; r.g = 0; r.h = 0; r.parent = -1;
-        r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0;
-        r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
-        nodes[0] = r;
-        htab_insert(htab, hmask, nodes, 0);
-        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, oge, nodes, n_, 0.0, 0); s_on = n_; }
-        }
-      }
-    }
-
-    // ---- main loop (path_planner.py:68-98)
-    bool reached = false;
-    AVP_TICK(0);                               // init + eager Dijkstra
-    for (;;) {
-      __syncthreads();
-      AVP_TICK(6);                             // commit (phase 5) of the previous iteration
-      if (tid == 0) {
-        if (dbg) { dbg[0] = 2; dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_on; }
-        if (P.watchdog_cycles > 0 && clock64() - t_start > P.watchdog_cycles && s_status == 0) s_status = AVP_CAPACITY;
-        if (s_status != 0 || s_on == 0) s_ctl = CTL_EXIT;
-        else if (s_npops >= cfg.max_pops) { s_status = AVP_CAPACITY; s_ctl = CTL_EXIT; }
-        else if (s_npops >= P.pop_budget) { s_status = AVP_PENDING; s_ctl = CTL_EXIT; }
-        else {
-          const int ret = s_oi[0];                     // open_list.get(): the root is the next node
-          s_cur = ret;
-          if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
-          s_npops++;
-          s_in_radius = nodes[ret].in_radius;
-          s_shot_coll = 0; s_shot_bad = 0; s_npts = 0; s_nplan = 0; s_best.ok = 0;
-          s_ctl = CTL_RUN;
-        }
-        for (int i = 0; i <= nchild; ++i) s_valid[i] = 0ull;
-      }
-      __syncthreads();
-      if (s_ctl == CTL_EXIT) break;
-      AVP_TICK(1);                             // loop top
-      const int cur = s_cur;
-      const Node cn = nodes[cur];
-      const int phi_np = cur != 0;           // root theta is a Python float (see oracle generate_path)
-
-      // phase 0: successor poses and the normalised rs queries (threads 32..)
-      {
-        const int t0 = (BLOCK >= 64) ? 32 : 0;       // keep thread 0's warp free for the heap
-        const int nsub = cfg.n_substeps <= 4 ? cfg.n_substeps : 4;
-        for (int item = tid - t0; item >= 0 && item < (nchild + 1) + nchild * nsub; item += BLOCK - t0) {
-          if (item <= nchild) {
-            const int c = item;
-            double q0[3];
-            if (c == nchild) { q0[0] = cn.x; q0[1] = cn.y; q0[2] = cn.theta; }
-            else { child_pose(cfg, cn, c, nchild, q0[0], q0[1], q0[2]); s_cpose[c][0] = q0[0]; s_cpose[c][1] = q0[1]; s_cpose[c][2] = q0[2]; }
-            if (c < nchild || s_in_radius) rs_query(q0, goal, maxc, s_Q[c]);
-          } else {
-            const int i = (item - nchild - 1) / nsub, k = (item - nchild - 1) % nsub;
-            const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-            const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-            const double td_i = speed * cfg.ddt * (k + 1);
-            const double th_i = pi_2_pi(cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-            const double cs = d_cos(th_i), sn = d_sin(th_i);
-            s_sub[i][k][0] = cn.x + td_i * cs; s_sub[i][k][1] = cn.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
-          }
-        }
-      }
-      __syncthreads();
-      AVP_TICK(2);                             // heappop + poses/queries
-      // phase 1: rs word instances: row nchild = the goal shot of the popped node, rows 0..nchild-1 = successors
-      // (speculative for successors that turn out skipped / colliding)
-      // item = inst * (nchild + 1) + row: the lanes of a warp evaluate the SAME word formula for different
-      // poses (instances of one family are adjacent), instead of 32 different formulas
-      // Thread 0 takes no item when the CTA is wide enough: it finishes heapq.heappop meanwhile (move the
-      // last entry to the root, sift) -- nothing in phases 1-4 touches the open heap.
-      constexpr int RS_T0 = (BLOCK >= 512) ? 1 : 0;
-      if (tid == 0) { const long long t_ = clock64(); int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_; pc[13] += clock64() - t_; pc[14] += n_; }
-      for (int item = tid - RS_T0; item >= 0 && item < (nchild + 1) * RS_NINST; item += BLOCK - RS_T0) {
-        const int inst = item / (nchild + 1), row = item - inst * (nchild + 1);
-        if (row == nchild && !s_in_radius) continue;
-        double t, u, v;
-        if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
-          RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
-          c.L = rs_cand_L(inst, c, 1, (row == nchild) ? phi_np : 1);
-          s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
-        }
-      }
-      __syncthreads();
-      AVP_TICK(3);                             // rs instances
-      // phase 2a, two groups of warps concurrently:
-      //   warps CW0..  : the successors' closed/open lookup and sub-step collision checks (hybrid_a_star.py:154-204)
-      //   warps 0..CW0-1: set_path de-duplication + minimum per (row, ctype group)
-      for (int i = warp - CW0; i >= 0 && i < nchild; i += NWARPS - CW0) {
-        const double x_ = s_cpose[i][0], y_ = s_cpose[i][1], th = s_cpose[i][2];
-        int found = -1, skip = 0;
-        if (lane == 0) {
-          found = htab_find(htab, hmask, nodes, x_, y_, th);
-          const bool in_closed = found >= 0 && nodes[found].in_closed;
-          const bool oob = (s_nclosed > 0) && (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
-          skip = (in_closed || oob) ? 1 : 0;
-          s_found[i] = found; s_skip[i] = skip; s_rsok[i] = 0; s_hv[i] = -1;
-        }
-        found = __shfl_sync(AVP_FULL_MASK, found, 0); skip = __shfl_sync(AVP_FULL_MASK, skip, 0);
-        int coll = 0;
-        if (!skip && found < 0) {
-          for (int k = 0; k < cfg.n_substeps; ++k) {
-            bool hit;
-            if (k < 4) hit = check_pose_cs_warp(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3]);
-            else {
-              const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
-              const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
-              const double td_i = speed * cfg.ddt * (k + 1);
-              const double th_i = pi_2_pi(cn.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-              hit = check_pose_warp(cfg, S, cells, col_start, cn.x + td_i * d_cos(th_i), cn.y + td_i * d_sin(th_i), th_i);
-            }
-            if (hit) { coll = 1; break; }
-          }
-        }
-        if (lane == 0) { s_coll[i] = coll; s_need[i] = (!skip) && ((found < 0 && !coll) || (found >= 0)); }
-      }
-      // phase 2a: set_path de-duplication + minimum per (row, ctype group) in parallel
-      for (int item = tid; tid < CW0 * 32 && item < (nchild + 1) * RS_NGROUP; item += CW0 * 32) {
-        const int g = item / (nchild + 1), row = item - g * (nchild + 1);       // group-major: same code path per warp
-        if (row == nchild && !s_in_radius) continue;          // successors: unconditionally (their collision flags are being computed concurrently)
-        rs_select_group(s_cand[row], s_valid[row], g, 1, (row == nchild) ? phi_np : 1, maxc, s_grp[row][g]);
-      }
-      __syncthreads();
-      // phase 2b: threads 0..nchild-1 combine the successors' groups (calc_optimal_path); another thread
-      //           combines the shot's, then lays out its segment origins and course plan
-      if (tid < nchild) {
-        if (s_need[tid]) {
-          RsBest b; rs_combine_groups(s_grp[tid], s_cand[tid], 1, 1, b);
-          s_rsok[tid] = (b.ok && !b.degenerate) ? 1 : 0;
-          s_rsL[tid] = b.ok ? b.L / maxc : 0.0;
-        }
-      }
-      {
-        // the shot's word, then its course plan (generate_local_course, rs_curve.py:537-594): lane 0 of the
-        // shot warp combines the groups; lanes 0..n-1 evaluate the segments' end-point increments in
-        // parallel (they only depend on the arc lengths); lane 0 accumulates the segment origins and
-        // records which (segment, arc length) writes each point index last.
-        constexpr int SHOT_WARP = (NWARPS > 1) ? 1 : 0;
-        if (warp == SHOT_WARP && s_in_radius) {
-          if (lane == 0) {
-            RsBest b; rs_combine_groups(s_grp[nchild], s_cand[nchild], 1, phi_np, b);
-            if (!b.ok || b.degenerate) s_shot_bad = 1;
-            else if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
-            s_best = b;
-          }
-          __syncwarp();
-          if (!s_shot_bad) {
-            const int nseg = s_best.n;
-            const char *mode = rs_ct_names[s_best.ct];
-            if (lane < nseg) {
-              double oyaw = 0.0;                                        // heading at the start of segment `lane`
-              for (int i = 0; i < lane; ++i) { if (mode[i] == 'L') oyaw = oyaw + s_best.len[i]; else if (mode[i] == 'R') oyaw = oyaw - s_best.len[i]; }
-              double ix, iy, yaw_next = oyaw; int dir;
-              rs_interpolate(s_best.len[lane], mode[lane], maxc, 0.0, 0.0, oyaw, ix, iy, yaw_next, dir);
-              s_org[lane + 1][0] = ix; s_org[lane + 1][1] = iy; s_org[lane + 1][2] = yaw_next;    // increments for now
-            }
-            __syncwarp();
-            if (lane == 0) {
-              const double step = 0.5 * maxc;
-              s_org[0][0] = 0.0; s_org[0][1] = 0.0; s_org[0][2] = 0.0;
-              for (int i = 0; i < nseg; ++i) { s_org[i + 1][0] = s_org[i][0] + s_org[i + 1][0]; s_org[i + 1][1] = s_org[i][1] + s_org[i + 1][1]; }
-              int ind = 1; double d, pd, ll = 0.0;
-              CYAW[0] = 0.0; CDIR[0] = -1;                    // point 0 is never written by interpolate
-              for (int i = 0; i < nseg; ++i) {
-                const double l = s_best.len[i];
-                d = (l > 0.0) ? step : -step;
-                ind -= 1;
-                if (i >= 1 && (s_best.len[i - 1] * s_best.len[i]) > 0) pd = -d - ll; else pd = d - ll;
-                while (fabs(pd) <= fabs(l) && ind + 2 < AVP_COURSE_CAP) { ind += 1; CYAW[ind] = pd; CDIR[ind] = i; pd += d; }
-                if (ind + 2 >= AVP_COURSE_CAP) { s_shot_bad = 2; break; }
-                ll = l - pd - d;
-                ind += 1; CYAW[ind] = l; CDIR[ind] = i;
-              }
-              s_nplan = ind + 1;
-            }
-          }
-        }
-      }
-      __syncthreads();
-      AVP_TICK(4);                             // lookups + collision checks || selection; combine + course plan
-      if (s_shot_bad) { if (tid == 0) s_status = (s_shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; continue; }
-
-      if (s_in_radius) {
-        // phase 3a: course points in parallel (rs_curve.py:597-624), local frame
-        const int nplan = s_nplan;
-        const char *mode = rs_ct_names[s_best.ct];
-        for (int j = tid; j < nplan; j += BLOCK) {
-          if (j == 0) { CX[0] = 0.0; CY[0] = 0.0; CYAW[0] = 0.0; CDIR[0] = (s_best.len[0] > 0.0) ? 1 : -1; continue; }
-          const int seg = CDIR[j]; const double l = CYAW[j];
-          double px, py, pyaw = 0.0; int dir;
-          rs_interpolate(l, mode[seg], maxc, s_org[seg][0], s_org[seg][1], s_org[seg][2], px, py, pyaw, dir);
-          if (mode[seg] == 'S') pyaw = s_org[seg][2];
-          CX[j] = px; CY[j] = py; CYAW[j] = pyaw; CDIR[j] = dir;
-        }
-        __syncthreads();
-        // phase 3b: drop trailing points whose local x is 0.0 (rs_curve.py:588-592), global transform (:124-130)
-        if (tid == 0) { int n = nplan; while (n > 0 && CX[n - 1] == 0.0) --n; s_npts = n; }
-        __syncthreads();
-        const int npts = s_npts;
-        const double cm = d_cos(-cn.theta), sm = d_sin(-cn.theta);
-        for (int j = tid; j < npts; j += BLOCK) {
-          const double ix = CX[j], iy = CY[j];
-          CX[j] = cm * ix + sm * iy + cn.x; CY[j] = -sm * ix + cm * iy + cn.y;
-          CYAW[j] = pi_2_pi(CYAW[j] + cn.theta);
-        }
-        __syncthreads();
-        // phase 3c: collision check of the course (hybrid_a_star.py:334-347)
-        for (int i = warp; i < npts; i += NWARPS) {
-          const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
-          if (stop) break;
-          if (check_pose_warp(cfg, S, cells, col_start, CX[i], CY[i], pi_2_pi(CYAW[i]))) { if (lane == 0) s_shot_coll = 1; }
-        }
-        __syncthreads();
-        if (!s_shot_coll) { reached = true; break; }                 // path_planner.py:86-88
-      }
-
-      AVP_TICK(5);                             // course points + shot collision check
-      // phase 4: commit preparation in parallel: node records, exact-pose table, g values, h-table prefetch
-      if (tid < nchild && !s_skip[tid]) {
-        const int i = tid, found = s_found[i];
-        const bool fwd = i < nchild / 2.0;
-        if (found < 0) {
-          const int child = s_G + i + 1;
-          if (child >= P.node_cap) s_status = AVP_CAPACITY;
-          else {
-            Node n; n.x = s_cpose[i][0]; n.y = s_cpose[i][1]; n.theta = s_cpose[i][2]; n.parent = cur;
-            n.g = s_coll[i] ? 0.0 : node_cost(cfg, fwd, n.theta, cn.theta, cn.forward != 0);    // :206-209
-            n.f = 0; n.h = 0;
-            n.forward = fwd ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num); n.in_open = 0;
-            n.in_closed = s_coll[i] ? 1 : 0; n.hpos = -1;
-            n.in_radius = s_coll[i] ? 0 : (sqrt(d_pow2(n.x - goal[0]) + d_pow2(n.y - goal[1])) < cfg.flag_radius);
-            nodes[child] = n;
-            s_g[i] = n.g;
-            __threadfence_block();
-            htab_insert(htab, hmask, nodes, child);
-          }
-        } else {
-          const Node &n = nodes[found];                                                      // :219-222
-          s_g[i] = node_cost(cfg, n.forward != 0, n.theta, cn.theta, cn.forward != 0);
-          s_oldf[i] = n.f;
-        }
-        if (s_need[i]) {
-          if (!s_rsok[i]) s_status = AVP_RS_DEGENERATE;
-          const long long id = map_index(S, s_cpose[i][0], s_cpose[i][1]);                 // calc_node_heuristic (:261-283)
-          s_hv[i] = (id >= 0 && id < S.n_ids) ? hval[id] : -1;
-          s_h1[i] = s_hv[i] / 100.0;                                                      // h_value_1 / 100 (:295)
-        }
-      }
-      __syncthreads();
-      AVP_TICK(7);                             // commit preparation
-
-      // phase 5: sequential commit in slot order (hybrid_a_star.py:154-239).  Lane 0 of warp 0 runs
-      // ahead over the successors whose h value is already in the table; a miss resumes the
-      // Dijkstra search, which is warp-collective.
-      if (warp == 0 && s_status == 0) {
-        int i = 0, n_miss = 0;
-        int on = s_on;                            // lane 0's register copy of the heap size
-        for (;;) {
-          int stop = nchild;
-          if (lane == 0) {
-            for (; i < nchild; ++i) {
-              if (s_skip[i]) continue;
-              if (s_found[i] < 0 && s_coll[i]) { s_nclosed++; continue; }
-              int hv = s_hv[i];
-              double h1 = s_h1[i];
-              if (n_miss > 0) {                    // a Dijkstra resume since the prefetch: re-read the table
-                const long long id = map_index(S, s_cpose[i][0], s_cpose[i][1]);
-                hv = (id >= 0 && id < S.n_ids) ? hval[id] : -1;
-                h1 = hv / 100.0;
-              }
-              if (hv < 0) break;                   // miss: needs the warp
-              s_nhcalls++;
-              const double h2 = s_rsL[i];
-              const double h = (h2 > h1) ? h2 : h1;                       // max(h_value_1, h_value_2) (:294-296)
-              const int found = s_found[i];
-              if (found < 0) {                                            // :206-216
-                const int child = s_G + i + 1;
-                Node &n = nodes[child];
-                const double f = s_g[i] + h;
-                n.h = h; n.f = f; n.in_open = 1;
-                { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; pc[12] += nodes[child].hpos; }
-              } else {                                                    // :219-230 (in place, no re-heapify)
-                const double new_f = h + s_g[i];
-                if (new_f < s_oldf[i]) {
-                  Node &n = nodes[found];
-                  n.f = new_f; n.g = s_g[i]; n.h = h; n.parent = cur; n.forward = (i < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(i % cfg.steering_angle_num);
-                  oh_set_key<SMO>(s_of, oge, n.hpos, new_f);
-                }
-              }
-            }
-            stop = i;
-          }
-          stop = __shfl_sync(AVP_FULL_MASK, stop, 0);
-          if (stop >= nchild) break;
-          // heuristic miss for successor `stop`: Dijkstra.compute_path resumes (compute_h.py:198-214)
-          long long term;
-          const long long td_ = clock64();
-          const int d = dij_compute_path(s_D, s_heap, s_cpose[stop][0], s_cpose[stop][1], &term);
-          if (lane == 0) { pc[10] += clock64() - td_; pc[11]++; }
-          ++n_miss;
-          if (lane == 0) {
-            if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
-            s_nhq++;
-            if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
-          }
-          __syncwarp();
-          if (__shfl_sync(AVP_FULL_MASK, s_status, 0)) break;
-          // the target cell is in the table now: lane 0 continues with successor `stop`
-        }
-        if (lane == 0) s_on = on;
-        if (lane == 0 && !s_status) { nodes[cur].in_closed = 1; nodes[cur].in_open = 0; s_nclosed++; s_G += nchild; }   // :235-239
-      }
-    }
-    __syncthreads();
-
-    // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
-    if (tid == 0) {
-      avp_plan_summary &R = P.sums[sc];
-      int status = s_status;
-      if (!status && !reached) status = (s_in_radius && s_best.ok) ? AVP_OPEN_EXHAUSTED_RS : AVP_OPEN_EXHAUSTED;
-      R.status = status; R.n_pops = s_npops; R.global_index = s_G; R.n_closed = s_nclosed; R.n_open = s_on;
-      R.last_index = s_cur; R.n_hq = s_nhq; R.h_closed = s_D.closed_len; R.nx = S.nx; R.ny = S.ny; R.n_obs = S.n_obs;
-      R.n_hcalls = s_nhcalls; R.pitch[0] = S.dx; R.pitch[1] = S.dy;
-      for (int i = 0; i < 4; ++i) R.boundary[i] = S.b[i];
-      R.origin[0] = S.b[0]; R.origin[1] = S.b[2];
-      R.n_astar = 0; R.n_rs = 0; R.n_final = 0; R.rs_nseg = 0; R.rs_L = 0.0;
-      for (int i = 0; i < 5; ++i) R.rs_lengths[i] = 0.0;
-      for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = 0;
-      if (status == AVP_OK || status == AVP_OPEN_EXHAUSTED_RS) {
-        double *fp = P.paths + (size_t)sc * P.cap_path * 3;
-        int np_ = 0;
-        int depth = 0; for (int k = s_cur; k != 0; k = nodes[k].parent) ++depth;
-        auto push = [&](double px, double py, double pt) { if (np_ < P.cap_path) { fp[3 * np_] = px; fp[3 * np_ + 1] = py; fp[3 * np_ + 2] = pt; } ++np_; };
-        push(nodes[0].x, nodes[0].y, nodes[0].theta);
-        for (int lvl = 1; lvl <= depth; ++lvl) {
-          int ch = s_cur; for (int k = 0; k < depth - lvl; ++k) ch = nodes[ch].parent;
-          const Node &c = nodes[ch]; const Node &par = nodes[c.parent];
-          for (int j = 0; j < cfg.n_substeps; ++j) {
-            const double speed = c.forward ? cfg.max_v : -cfg.max_v;
-            const double td_j = speed * cfg.ddt * (j + 1);
-            const double th_j = pi_2_pi(par.theta + (cfg.max_v * cfg.tan_steer[c.steer_idx]) / cfg.lw * cfg.ddt * (j + 1));
-            push(par.x + td_j * d_cos(th_j), par.y + td_j * d_sin(th_j), th_j);
-          }
-        }
-        R.n_astar = np_;
-        for (int i = 1; i < s_npts; ++i) push(CX[i], CY[i], CYAW[i]);
-        R.n_final = np_; R.n_rs = s_npts; R.rs_nseg = s_best.n; R.rs_L = s_best.L / maxc;
-        for (int i = 0; i < s_best.n; ++i) R.rs_lengths[i] = s_best.len[i] / maxc;
-        for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = rs_ct_names[s_best.ct][i];
-      }
-      if (dbg) dbg[0] = 9;
-      if (P.prof) for (int k = 0; k < 16; ++k) P.prof[(size_t)sc * 16 + k] = pc[k];
-    }
-    __syncthreads();
-  }
-}

@@ -1,92 +1,129 @@
-// avp_search_pipe.cuh -- the pipelined search kernel for the long tail (pass 2).
+// avp_plan.cuh -- PathPlanner.a_star_plan (path_planner.py:58-110) for a whole batch: ONE persistent launch.
 //
-// PathPlanner.a_star_plan (path_planner.py:58-110) has two kinds of work per popped node:
+//   k_plan_init   run queue, slot pool and counters of the launch (device side, no host data)
+//   k_dij_eager   hybrid_a_star.__init__'s eager Dijkstra.compute_path(x0, y0) (hybrid_a_star.py:89-91) for every
+//                 scenario: one WARP per scenario (the heapq emulation of avp_kernels.cuh is a one-warp algorithm),
+//                 twenty warps per SM, the queue left in the scenario's own heap array where k_plan resumes it
+//   k_plan        the searches.  One CTA works on one scenario at a time: warp 0 commits, the other warps evaluate the
+//                 node that will be popped next (the pipelined pop, avp_pipe_defs.cuh).  What is new is
+//                 the scheduling around it:
 //
-//   PURE    a function of the node's pose only: the 10 successor poses (hybrid_a_star.py:134-151), their
-//           sub-step collision checks (:185-204), their rs lengths (:286-292) and the goal shot of the node
-//           itself (try_rs_curve, :318-349).
-//   COMMIT  order dependent: closed/open lookups (:154-172), node creation, the Dijkstra term of the
-//           heuristic (history dependent, compute_h.py:198-214), heap pushes / in-place updates (:206-230)
-//           and the next open_list.get() (path_planner.py:70).
-//
-// k_search evaluates both one after the other for every pop.  Here warp 0 (the COMMIT warp) runs the
-// reference's sequential loop while warps 1.. (the EVALUATORS) compute the PURE part of the node that
-// will be popped next, one step ahead.  The next node is predicted after the lookups of the current
-// commit: it is the first successor with the smallest f if that f is below the f of the heap root, else
-// the heap root -- exactly what the pushes of this commit produce, unless a successor's Dijkstra value
-// is not in the table yet (then the prediction may miss).  A miss costs one un-overlapped evaluation;
-// results never depend on the prediction (a PURE result is only used for the node it was computed for).
-//
-//   barrier A | C: accept the result of the popped node; lookups (lanes 0..9, probes read ahead by    | barrier B
-//             |    the evaluators); predict the next pop; publish it as the evaluators' target and       |
-//             |    initialise their queue                                                             |
-//   barrier B | C: node records, sequential commit in slot order (Dijkstra resumes inside), heappop,  | barrier A
-//             |    then it takes E1 items if any are left                                             |
-//             | E: ONE dependency-ordered queue of warp items (see E1 / E2 below)                     |
-//
-// The evaluation is a single queue of warp items without a barrier inside: items whose inputs come from
-// other items (rs words <- successor poses, sub-step checks <- sub-step poses, course point checks <-
-// course plan, word selection <- all rs items, table probes <- the commit warp's inserts) sit behind their
-// producers in the queue and wait on a shared-memory flag / counter (release / acquire at CTA scope).  A
-// producer never waits, so the queue cannot dead-lock.  A and B are __syncthreads(), the only barriers
-// of a pop.
-// The word of the goal shot is the word selected when the node was scored (NodeShot), so the shot costs
-// no rs solve; its course is planned by the first queue item and its points are collision-checked by
-// whichever warps run out of rs / sub-step items first.
-// The exact-pose table probes and h-table reads of the NEXT commit's lookups are issued by the evaluators
-// (item 3) as soon as the running commit has finished its table inserts: the DRAM round trips of the
-// lookups leave the serial section between A and B (7-8 k -> 4.5 k cycles per pop).
+// * A search is RESUMABLE.  Everything it owns lives in global memory -- per scenario: h table, Dijkstra queue, counters
+//   (ScenState); per slot: nodes, open heap, exact-pose table -- and the shared-memory heads of the two heaps are written
+//   back when a CTA lets go of it.  No pass barrier, no host round trip, nothing is planned twice.
+// * ONE run queue (a ring of scenario ids, longest start-goal distance first).  A CTA takes the head, runs it for a
+//   QUANTUM of pops and, if the search is still going and somebody is waiting, appends it to the tail: round robin.
+//   Short searches (the median is 19 pops) leave the system in their first quantum; the long ones -- on the bench
+//   workload 5 % of the scenarios hold 78 % of the pops -- share the SMs fairly from the first millisecond instead of
+//   queueing behind each other.
+// * SM pairs.  The two SMs of a TPC share instruction-fetch resources and this kernel is fetch bound (profiles/): a
+//   search runs 25-30 % faster beside an idle neighbour.  While more scenarios are live than 1.5 per pair every CTA
+//   works; below that the CTAs on odd SM ids stop taking work (P.spread).
 #pragma once
-#include "avp_kernels.cuh"
+#include "avp_pipe_defs.cuh"
 
-enum { CTL_FINISH = 2 };
-
-// The rs warp items of the E1 queue: up to three word instances per item (lanes = instance slot x successor), formed so
-// that a warp runs one word formula where possible (4 instances per family: 3 + 1 left over).  Ordered by measured cost,
-// longest first (profiles/: 21 k ... 3 k cycles per item); a left-over item with three different formulas costs the sum of
-// the three (41 k cycles for {9,29,37}), so those instances are items of their own.
-#define RS_NITEM 19
-__device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
-  {45, 13, 17}, {0, 1, -1}, {6, 7, 8}, {5, 33, 41}, {20, 21, -1}, {22, 23, -1}, {10, 11, 12}, {14, 15, 16}, {26, 27, 28},
-  {34, 35, 36}, {24, 25, -1}, {9, -1, -1}, {29, -1, -1}, {37, -1, -1}, {2, 3, 4}, {38, 39, 40}, {30, 31, 32}, {42, 43, 44}, {18, 19, -1}};
-
-struct PureRes {
-  double cpose[AVP_NCHILD_MAX][3];
-  int32_t found[AVP_NCHILD_MAX], hv[AVP_NCHILD_MAX];     // exact-pose table probe and h-table value, read ahead by the evaluators (see E2)
-  double rsL[AVP_NCHILD_MAX];
-  NodeShot shot[AVP_NCHILD_MAX];
-  int32_t coll[AVP_NCHILD_MAX], rsok[AVP_NCHILD_MAX], inrad[AVP_NCHILD_MAX], hid[AVP_NCHILD_MAX];
-  int32_t node;                              // the node this result belongs to (-1: none)
-  int32_t in_radius, shot_ok;                // the shot's collision / degeneracy flags stay in shared memory (s_shot_coll, s_shot_bad)
+// per scenario: what a suspended search needs besides its slot
+struct __align__(16) ScenState {
+  int32_t phase;                 // 0 new (eager Dijkstra done), 1 suspended, 2 final
+  int32_t slot;                  // workspace slot (-1: none yet)
+  int32_t status;                // status the eager Dijkstra ended with (0: go on)
+  int32_t dij_hn, dij_closed;    // Dijkstra queue length, len(closedlist)
+  int32_t nhq, nhcalls, G, nclosed, npops, on, cur, in_radius, best_ok;
+  int32_t quanta, pad;
 };
-struct EvalTarget { double x, y, theta; NodeShot shot; int32_t node, in_radius, is_root, valid; };
+struct PlanCtl { int q_head, q_tail, finalised, slot_head, slot_tail, n_suspends, n_requeues, error; };
 
-// clock read that the compiler may not move across barriers or memory operations (profiling counters)
-__device__ __forceinline__ long long clock_ordered() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+struct PlanParams {
+  KParams K;                     // cfg, scenario arrays, results (work_list = initial order of the run queue)
+  ScenState *state;
+  PlanCtl *ctl;
+  int32_t *queue; int q_mask;    // ring of scenario ids, -1 = empty cell
+  int32_t *slot_ring; int slot_mask; int n_slots;
+  int quantum;                   // pops per turn while others wait
+  int spread_max;                // the CTAs on odd SM ids only work while more scenarios than this are live (P.K.spread)
+};
 
-
-// CTA-scope release / acquire on shared-memory words: the hand-off between producers and consumers of the evaluators'
-// queue (the payload is written with plain stores before the release and read with plain loads after the acquire).
-__device__ __forceinline__ void st_release_cta(int *p, int v) { asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire_cta(const int *p) { int v; asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory"); return v; }
-// wait until *p >= want.  A producer never waits (see the header), so this returns after a bounded time; the guard
-// (2^27 cycles, three orders of magnitude above any real wait) turns a protocol bug into an error status instead of a hang.
-__device__ __forceinline__ bool wait_ge_cta(const int *p, int want) {
-  if (ld_acquire_cta(p) >= want) return true;
-  const long long t0 = clock64();
-  for (int k = 1;; ++k) {
-    if (ld_acquire_cta(p) >= want) return true;
-    if ((k & 255) == 0 && clock64() - t0 > (1ll << 27)) return false;
-#ifdef AVP_SPIN_SLEEP        // A/B build: the polls are 8 % of the kernel's issued instructions (profiles/hot_footprint_r01d.txt)
-    __nanosleep(AVP_SPIN_SLEEP);
-#endif
+// multi-producer / multi-consumer ring of non-negative ints; at most (mask + 1) entries are ever in flight, so a cell is
+// empty again before its index comes round.  Called by ONE thread of a CTA.
+__device__ __forceinline__ int ring_pop(int *head, int *tail, int32_t *buf, int mask) {
+  for (;;) {
+    const int h = *(volatile int *)head, t = *(volatile int *)tail;
+    if (h - t >= 0) return -1;
+    if (atomicCAS(head, h, h + 1) == h) {
+      int v; long long spins = 0;
+      while ((v = atomicExch(&buf[h & mask], -1)) == -1) { if (++spins > (1ll << 28)) return -3; }     // the producer has reserved the cell and writes it next (the bound turns a protocol bug into an error, not a hang)
+      __threadfence();                                                // acquire: the producer's state is visible to this CTA
+      return v;
+    }
   }
 }
-__device__ __forceinline__ void add_release_cta(int *p, int v) { asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory"); }
+__device__ __forceinline__ void ring_push(int *tail, int32_t *buf, int mask, int v) {
+  __threadfence();                                                    // release: everything written for the consumer
+  const int t = atomicAdd(tail, 1);
+  long long spins = 0;
+  while (atomicCAS(&buf[t & mask], -1, v) != -1) { if (++spins > (1ll << 28)) return; }
+}
+
+__global__ void k_plan_init(PlanParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= P.q_mask) P.queue[i] = (i < P.K.n_work) ? (P.K.work_list ? P.K.work_list[i] : i) : -1;
+  if (i <= P.slot_mask) P.slot_ring[i] = (i < P.n_slots) ? i : -1;
+  if (i == 0) { PlanCtl c; c.q_head = 0; c.q_tail = P.K.n_work; c.finalised = 0; c.slot_head = 0; c.slot_tail = P.n_slots; c.n_suspends = 0; c.n_requeues = 0; c.error = 0; *P.ctl = c; *P.K.work_counter = 0; }
+}
+
+#define AVP_DIJ_WARPS 4
+// one warp per scenario, persistent warps pulling scenarios (longest first) from an atomic counter
+__global__ void __launch_bounds__(AVP_DIJ_WARPS * 32) k_dij_eager(PlanParams P) {
+  __shared__ unsigned long long s_heap[AVP_DIJ_WARPS][AVP_SM_HEAP];
+  __shared__ DijCtx s_D[AVP_DIJ_WARPS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const KParams &K = P.K;
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(K.work_counter, 1);
+    it = __shfl_sync(AVP_FULL_MASK, it, 0);
+    if (it >= K.n_work) break;
+    const int sc = K.work_list ? K.work_list[it] : it;
+    const ScenDev &S = K.scen[sc];
+    int32_t *hval = K.hval + S.id_off, *ost = K.ost + S.id_off;
+    unsigned long long *gheap = K.dheap + (size_t)sc * K.dheap_cap;
+    for (int i = lane; i < S.n_ids; i += 32) { hval[i] = -1; ost[i] = -1; }
+    DijCtx &D = s_D[w];
+    if (lane == 0) {
+      D.S = &S; D.cost = K.cost + S.cost_off; D.hval = hval; D.ost = ost; D.gx = K.gx + S.id_off; D.gy = K.gy + S.id_off;
+      D.sheap = s_heap[w]; D.gheap = gheap; D.gcap = K.dheap_cap; D.hn = 0; D.closed_len = 0; D.status = 0;
+    }
+    __syncwarp();
+    int status = S.raster_error ? AVP_RASTER_AMBIGUOUS : 0, nhq = 0;
+    if (!status) {
+      long long term;
+      const int d = dij_compute_path(D, s_heap[w], S.pose[0], S.pose[1], &term);
+      __syncwarp();
+      if (lane == 0 && K.hq_log) { int32_t *hql = K.hq_log + (size_t)sc * AVP_HQ_CAP * 3; hql[0] = (int)term; hql[1] = d; hql[2] = D.closed_len; }
+      nhq = 1;
+      if (d < 0) status = D.status ? D.status : AVP_H_UNREACHABLE;     // the reference never returns from this compute_path: no root node
+    }
+    const int hn = D.hn;
+    for (int i = lane; i < hn && i < AVP_SM_HEAP; i += 32) gheap[i] = s_heap[w][i];
+    if (lane == 0) {
+      ScenState st; st.phase = 0; st.slot = -1; st.status = status; st.dij_hn = hn; st.dij_closed = D.closed_len;
+      st.nhq = nhq; st.nhcalls = 0; st.G = 0; st.nclosed = 0; st.npops = 0; st.on = 0; st.cur = -1; st.in_radius = 0; st.best_ok = 0; st.quanta = 0; st.pad = 0;
+      P.state[sc] = st;
+    }
+    __syncwarp();
+  }
+}
+
+#ifdef AVP_PROFILE
+#define PROF(...) __VA_ARGS__
+#else
+#define PROF(...)
+#endif
 
 template <int BLOCK>
-__device__ __forceinline__ void search_pipe_body(const KParams &P) {
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
   static_assert(BLOCK >= 128 && BLOCK % 32 == 0, "one commit warp + at least three evaluator warps");
+  const KParams &P = PP.K;
   constexpr int SMO = avp_sm_open(BLOCK);
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double *s_of = reinterpret_cast<double *>(s_dyn);
@@ -104,161 +141,165 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
   __shared__ double s_tcs[2];
   __shared__ double s_g[AVP_NCHILD_MAX], s_oldf[AVP_NCHILD_MAX], s_h1[AVP_NCHILD_MAX];
   __shared__ int s_found[AVP_NCHILD_MAX], s_need[AVP_NCHILD_MAX], s_skip[AVP_NCHILD_MAX], s_hv[AVP_NCHILD_MAX];
-  __shared__ int s_trace_on;
   __shared__ int s_chit[AVP_NCHILD_MAX];
-  __shared__ int s_scen, s_ctlA, s_ctlB, s_cur, s_do_commit, s_rb, s_nplan, s_npts, s_shot_coll, s_shot_bad, s_work;
+  __shared__ int s_scen, s_slot, s_phase, s_odd, s_limit;
+  __shared__ int s_ctlA, s_ctlB, s_cur, s_do_commit, s_rb, s_nplan, s_npts, s_shot_coll, s_shot_bad, s_work;
   __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls, s_on, s_in_radius, s_best_ok;
   __shared__ int s_work2, s_work3, s_rs_done, s_course_rdy, s_q_rdy, s_sub_rdy, s_ins_done, s_cstride;   // the evaluators' queue: tail counter, finished rs items, course / rs queries / sub-step poses published, table inserts of the running commit done, stride of the course point order
   __shared__ VehGeom s_vg[BLOCK / 32];           // per warp: the vehicle rectangle of the pose being checked (check_distance_warp_sm)
   __shared__ DijCtx s_D;
-  __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts), development aid
+#ifdef AVP_PROFILE
+  __shared__ int s_trace_on;
+  __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts)
   __shared__ long long s_wp[BLOCK / 32][8];   // per warp: cycles lane 0 spent working in each evaluator phase (barrier waits excluded)
+#endif
 
   const avp_config &cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = (int)blockIdx.x;
   const int nchild = 2 * cfg.steering_angle_num;
   const double maxc = 1 / cfg.min_radius_turn;
-  Node *nodes = P.nodes + (size_t)slot * P.node_cap;
-  NodeShot *nshot = P.nshot + (size_t)slot * P.node_cap;
-  int32_t *htab = P.htab + (size_t)slot * P.htab_stride;
-  OEnt *oge = P.oheap + (size_t)slot * P.node_cap;
   const int hmask = P.htab_size - 1;
-  double *CX = P.course + (size_t)slot * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
-  int32_t *CDIR = P.course_dir + (size_t)slot * AVP_COURSE_CAP;
+  double *CX = P.course + (size_t)blockIdx.x * 3 * AVP_COURSE_CAP, *CY = CX + AVP_COURSE_CAP, *CYAW = CY + AVP_COURSE_CAP;
+  int32_t *CDIR = P.course_dir + (size_t)blockIdx.x * AVP_COURSE_CAP;
+  PlanCtl *ctl = PP.ctl;
 
-  // P.spread: the grid has one CTA per SM of the device although there is less work than SMs, and the CTAs on odd SM ids
-  // leave the work to the even ones: each scenario then has an SM pair (TPC) to itself.  The kernel is instruction-fetch
-  // bound and the pair shares fetch resources: a 20 000-pop scenario takes 1.43 G cycles with an idle neighbour SM, 1.9 G
-  // beside another such scenario (profiles/).  An odd CTA only watches the work counter: it leaves when every item is taken,
-  // and takes items itself if the counter has not moved for ~0.5 s (no even CTA resident, e.g. on a shared device).
-  if (P.spread) {
+  if (tid == 0) { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); s_odd = (int)(sm_ & 1u); }
+
+  for (;;) {
+    // ---- take the head of the run queue (thread 0).  The CTAs on odd SM ids stand back while few scenarios are live (see the
+    //      header); if the live count has not moved for ~0.25 s they work anyway (no even CTA resident, e.g. a shared device).
     if (tid == 0) {
-      unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_));
-      int go = 1;
-      if (sm_ & 1u) {
-        go = 0;
-        long long t_last = clock64(); int last = -1;
-        for (;;) {
-          const int c = *(volatile int *)P.work_counter;
-          if (c >= P.n_work) break;
-          if (c != last) { last = c; t_last = clock64(); }
-          else if (clock64() - t_last > 1000000000ll) { go = 1; break; }
-          __nanosleep(20000);
+      int got = -1;
+      long long t_last = clock64(); int last = -1; const long long t_idle = t_last;
+      for (;;) {
+        const int fin = *(volatile int *)&ctl->finalised;
+        if (fin >= P.n_work) break;
+        bool allowed = !(P.spread && s_odd) || (P.n_work - fin > PP.spread_max);
+        if (!allowed) {
+          if (fin != last) { last = fin; t_last = clock64(); }
+          else if (clock64() - t_last > 500000000ll) allowed = true;
+        }
+        if (allowed) { got = ring_pop(&ctl->q_head, &ctl->q_tail, PP.queue, PP.q_mask); if (got >= 0) break; if (got == -3) { atomicExch(&ctl->error, 1); got = -1; break; } }
+        if (clock64() - t_idle > (1ll << 38)) { atomicExch(&ctl->error, 2); got = -1; break; }      // ~2 minutes without work while searches are unfinished: give up (the host reports it)
+        __nanosleep(allowed ? 500 : 5000);
+      }
+      int slot = -1, phase = 0;
+      if (got >= 0) {
+        const int4 st = __ldcg(reinterpret_cast<const int4 *>(&PP.state[got]));     // phase, slot, status, dij_hn
+        phase = st.x; slot = st.y;
+        if (phase == 0 && st.z == 0) {
+          slot = ring_pop(&ctl->slot_head, &ctl->slot_tail, PP.slot_ring, PP.slot_mask);
+          if (slot < 0) {       // every slot is held by a suspended search: this one goes to the back of the queue, a suspended one will come up
+            ring_push(&ctl->q_tail, PP.queue, PP.q_mask, got); atomicAdd(&ctl->n_requeues, 1); got = -2; __nanosleep(2000);
+          }
         }
       }
-      s_scen = go;
+      s_scen = got; s_slot = slot; s_phase = phase;
     }
     __syncthreads();
-    if (!s_scen) return;
-    __syncthreads();
-  }
-  for (;;) {
-    if (tid == 0) s_scen = atomicAdd(P.work_counter, 1);
-    __syncthreads();
-    const int scen_i = s_scen;
-    if (scen_i >= P.n_work) break;
-    const int sc = P.work_list ? P.work_list[scen_i] : scen_i;
+    const int sc = s_scen;
+    if (sc == -1) break;
+    if (sc == -2) { __syncthreads(); continue; }
+    const int slot = s_slot;
+    const bool fresh = (s_phase == 0);
+    Node *nodes = P.nodes + (size_t)(slot < 0 ? 0 : slot) * P.node_cap;
+    NodeShot *nshot = P.nshot + (size_t)(slot < 0 ? 0 : slot) * P.node_cap;
+    int32_t *htab = P.htab + (size_t)(slot < 0 ? 0 : slot) * P.htab_stride;
+    OEnt *oge = P.oheap + (size_t)(slot < 0 ? 0 : slot) * P.node_cap;
     const ScenDev &S = P.scen[sc];
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
     int32_t *hval = P.hval + S.id_off, *ost = P.ost + S.id_off;
+    unsigned long long *dgheap = P.dheap + (size_t)sc * P.dheap_cap;
     const double goal[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
     int32_t *pops = P.pops ? P.pops + (size_t)sc * P.cap_pops : nullptr;
     int32_t *hql = P.hq_log ? P.hq_log + (size_t)sc * AVP_HQ_CAP * 3 : nullptr;
     int *dbg = P.dbg ? P.dbg + (size_t)sc * 8 : nullptr;
     const long long t_start = clock64();
+#ifdef AVP_PROFILE
     // cycle accumulators: thread 0 (commit warp) and thread 32 (evaluators) each keep their own
     long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
-#ifdef AVP_NO_PROFILE        // A/B build without the cycle counters in the hot loop (the profile outputs stay zero)
-#define PIPE_TICK(who, k) do { } while (0)
-#else
-#define PIPE_TICK(who, k) do { if (tid == (who)) { const long long t_ = clock_ordered(); pc[k] += t_ - tp; tp = t_; } } while (0)
-#endif
     long long wt = 0;
-#ifdef AVP_NO_PROFILE
-#define WP_START() do { } while (0)
-#define WP_ACC(k) do { } while (0)
-#else
+#define PIPE_TICK(who, k) do { if (tid == (who)) { const long long t_ = clock_ordered(); pc[k] += t_ - tp; tp = t_; } } while (0)
 #define WP_START() do { if (lane == 0) wt = clock_ordered(); } while (0)
 #define WP_ACC(k) do { if (lane == 0) { const long long t_ = clock_ordered(); s_wp[warp][k] += t_ - wt; wt = t_; } } while (0)
-#endif
     if (lane == 0) for (int k = 0; k < 8; ++k) s_wp[warp][k] = 0;
     if (tid < 48) s_ic[tid] = 0;
-    // timeline of ONE pop (the AVP_TRACE_POP-th of the scenario): absolute clocks of every warp at the phase boundaries
     long long *tsw = (P.wprof && warp < 16) ? P.wprof + ((size_t)sc * 16 + warp) * 24 + 8 : nullptr;
-#ifdef AVP_NO_PROFILE
-#define TS(k) do { } while (0)
-#else
 #define TS(k) do { __syncwarp(); if (lane == 0 && tsw && ((k) < 2 ? (s_npops == P.trace_pop) : s_trace_on)) tsw[k] = clock_ordered(); } while (0)
+#else
+#define PIPE_TICK(who, k) do { } while (0)
+#define WP_START() do { } while (0)
+#define WP_ACC(k) do { } while (0)
+#define TS(k) do { } while (0)
 #endif
 
     // open_list.get() (path_planner.py:70) with the loop's exit tests; lane 0 of the commit warp
     auto do_pop = [&]() {
       if (dbg) { dbg[0] = 2; dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_on; }
       if (P.watchdog_cycles > 0 && clock64() - t_start > P.watchdog_cycles && s_status == 0) s_status = AVP_CAPACITY;
-      if (s_status != 0 || s_on == 0) s_ctlA = CTL_EXIT;
-      else if (s_npops >= cfg.max_pops) { s_status = AVP_CAPACITY; s_ctlA = CTL_EXIT; }
-      else if (s_npops >= P.pop_budget) { s_status = AVP_PENDING; s_ctlA = CTL_EXIT; }
-      else {
-        const int ret = s_oi[0];
-        s_cur = ret;
-        if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
-        s_npops++;
-        int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_;
-        s_ctlA = CTL_RUN;
+      if (s_status != 0 || s_on == 0) { s_ctlA = CTL_EXIT; return; }
+      if (s_npops >= cfg.max_pops) { s_status = AVP_CAPACITY; s_ctlA = CTL_EXIT; return; }
+      if (s_npops >= s_limit) {
+        // the quantum is used up: let go of the scenario if another one waits for an SM, or if this CTA sits on an odd SM id
+        // and should stand back by now (an even CTA will take it); else run on without saving anything
+        const int fin = *(volatile int *)&ctl->finalised;
+        const bool waiting = (*(volatile int *)&ctl->q_head - *(volatile int *)&ctl->q_tail) < 0;
+        const bool stand_back = P.spread && s_odd && (P.n_work - fin <= PP.spread_max);
+        if (waiting || stand_back) { s_status = AVP_PENDING; s_ctlA = CTL_EXIT; return; }
+        s_limit = s_npops + PP.quantum;
       }
+      const int ret = s_oi[0];
+      s_cur = ret;
+      if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
+      s_npops++;
+      int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_;
+      s_ctlA = CTL_RUN;
     };
 
-    // ---- per-scenario initialisation (all threads)
-    for (int i = tid; i < S.n_ids; i += BLOCK) { hval[i] = -1; ost[i] = -1; }
-    for (int i = tid; i < P.htab_size; i += BLOCK) htab[i] = -1;
+    // ---- take over the scenario: a fresh one starts at the root (the eager Dijkstra is done: k_dij_eager), a suspended one where
+    //      it was left.  The shared-memory heads of the two heaps come from their save areas.
+    const ScenState st0 = PP.state[sc];
+    if (fresh && slot >= 0) for (int i = tid; i < P.htab_size; i += BLOCK) htab[i] = -1;
+    for (int i = tid; i < st0.dij_hn && i < AVP_SM_HEAP; i += BLOCK) s_heap[i] = dgheap[i];
+    if (!fresh) for (int i = tid; i < st0.on && i < SMO; i += BLOCK) { const int4 v = *reinterpret_cast<const int4 *>(&oge[i]); s_of[i] = __hiloint2double(v.y, v.x); s_oi[i] = v.z; }
     if (tid == 0) {
       s_D.S = &S; s_D.cost = P.cost + S.cost_off; s_D.hval = hval; s_D.ost = ost;
       s_D.gx = P.gx + S.id_off; s_D.gy = P.gy + S.id_off;
-      s_D.sheap = s_heap; s_D.gheap = P.dheap + (size_t)slot * P.dheap_cap; s_D.gcap = P.dheap_cap;
-      s_D.hn = 0; s_D.closed_len = 0; s_D.status = 0;
-      s_on = 0;
-      s_G = 0; s_nclosed = 0; s_npops = 0; s_nhq = 0; s_nhcalls = 0;
-      s_status = S.raster_error ? AVP_RASTER_AMBIGUOUS : 0;
-      s_cur = -1; s_in_radius = 0; s_best_ok = 0; s_shot_coll = 0; s_npts = 0; s_best.ok = 0;
+      s_D.sheap = s_heap; s_D.gheap = dgheap; s_D.gcap = P.dheap_cap;
+      s_D.hn = st0.dij_hn; s_D.closed_len = st0.dij_closed; s_D.status = 0;
+      s_on = st0.on; s_G = st0.G; s_nclosed = st0.nclosed; s_npops = st0.npops; s_nhq = st0.nhq; s_nhcalls = st0.nhcalls;
+      s_status = st0.status;
+      s_cur = st0.cur; s_in_radius = st0.in_radius; s_best_ok = st0.best_ok; s_shot_coll = 0; s_npts = 0; s_best.ok = 0;
       s_res[0].node = -1; s_res[1].node = -1; s_rb = 0; s_do_commit = 0; s_ctlA = CTL_RUN; s_ctlB = CTL_RUN;
       s_best.ct = 0; s_best.n = 0; s_best.inst = -1; s_best.degenerate = 0; s_best.L = 0.0;
-      if (dbg) { dbg[0] = 1; dbg[1] = 0; }
+      s_limit = st0.npops + PP.quantum;
+      if (dbg) { dbg[0] = 1; dbg[1] = st0.npops; }
     }
     __syncthreads();
-
-    // ---- hybrid_a_star.__init__: eager Dijkstra to the start cell (hybrid_a_star.py:89-91), root node (:102-112);
-    //      warp 1 meanwhile solves the root's rs word (the root's theta is a Python float: phi_np = 0)
-    if (warp == 0 && s_status == 0) {
-      long long term;
-      const int d = dij_compute_path(s_D, s_heap, S.pose[0], S.pose[1], &term);
-      if (lane == 0) {
-        if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
-        s_nhq++;
-        if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;     // the reference never returns from this compute_path: no root node
-        else {
+    if (fresh && s_status == 0) {
+      // root node (hybrid_a_star.py:102-112); warp 1 meanwhile solves the root's rs word (the root's theta is a Python float: phi_np = 0)
+      if (tid == 0) {
         Node r; r.x = S.pose[0]; r.y = S.pose[1]; r.theta = pi_2_pi(S.pose[2]); r.f = 0; r.g = 0; r.h = 0; r.parent = -1;
         r.forward = 1; r.steer_idx = 0; r.in_open = 1; r.in_closed = 0; r.hpos = 0;
         r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
         { int n_ = s_on; oh_push<SMO>(s_of, s_oi, oge, nodes, n_, 0.0, 0); s_on = n_; }
+      } else if (warp == 1) {
+        const double q0[3] = {S.pose[0], S.pose[1], pi_2_pi(S.pose[2])};
+        RsBest b; rs_length_warp(q0, goal, maxc, 1, 0, s_cand[0], b);
+        if (lane == 0) {
+          NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
+          if (b.ok && !b.degenerate) { w.t = s_cand[0][b.inst].t; w.u = s_cand[0][b.inst].u; w.v = s_cand[0][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = 1; }
+          nshot[0] = w;
         }
-      }
-    } else if (warp == 1) {
-      const double q0[3] = {S.pose[0], S.pose[1], pi_2_pi(S.pose[2])};
-      RsBest b; rs_length_warp(q0, goal, maxc, 1, 0, s_cand[0], b);
-      if (lane == 0) {
-        NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
-        if (b.ok && !b.degenerate) { w.t = s_cand[0][b.inst].t; w.u = s_cand[0][b.inst].u; w.v = s_cand[0][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = 1; }
-        nshot[0] = w;
       }
     }
     __syncthreads();
-    if (tid == 0) do_pop();                      // the first get() returns the root
-    PIPE_TICK(0, 0);                             // init + eager Dijkstra
-    if (tid == 32) tp = clock_ordered();
+    if (tid == 0) do_pop();                      // a fresh search: the first get() returns the root
+    PIPE_TICK(0, 0);
+    PROF(if (tid == 32) tp = clock_ordered();)
 
     bool reached = false;
     for (;;) {
@@ -272,38 +313,51 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         WP_START();
         const int wb = s_rb ^ 1;
         const int cur = s_cur;
-        if (lane == 0) { s_ctlB = CTL_RUN; s_trace_on = (s_npops == P.trace_pop); }
+        if (lane == 0) { s_ctlB = CTL_RUN; PROF(s_trace_on = (s_npops == P.trace_pop);) }
         __syncwarp();
         if (s_res[wb].node == cur) {             // the result of the popped node is there
           PureRes &R = s_res[wb];
           const int shot_bad = R.in_radius ? s_shot_bad : 0, shot_coll = R.in_radius ? s_shot_coll : 0;   // of the evaluation just finished
           if (lane < nchild) R.coll[lane] = s_chit[lane];          // sub-step collision flags of the evaluation just finished
-          if (lane == 0) { s_rb = wb; s_in_radius = R.in_radius; s_best_ok = R.shot_ok; pc[5]++; }
+          if (lane == 0) { s_rb = wb; s_in_radius = R.in_radius; s_best_ok = R.shot_ok; PROF(pc[5]++;) }
           __syncwarp();
           if (shot_bad) { if (lane == 0) { s_status = (shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; s_ctlB = CTL_EXIT; } }
           else if (R.in_radius && !shot_coll) { if (lane == 0) s_ctlB = CTL_FINISH; }     // path_planner.py:86-88
           else {
             // ---- lookups, g values, h-table prefetch (hybrid_a_star.py:154-172, :206-222): lanes 0..nchild-1.
             //      Node records and table inserts follow after barrier B (the evaluators do not need them).
-            int found = -1, skip = 1, coll = 0;
+            int found = -1, skip = 1, coll = 0; bool in_closed = false, oob_geo = false;
+            const Node cn = nodes[cur];
+            int hvp = -1;
             if (lane < nchild) {
               const int i = lane;
               const int id = R.hid[i];
               // probe and h value were read ahead by the evaluators (E2) after the table inserts of the commit that ran beside
               // them: no insert and no Dijkstra resume has happened since, except that an h value missing then may be there now
-              int hvp = R.hv[i];
+              hvp = R.hv[i];
               if (hvp < 0 && id >= 0) hvp = hval[id];
-              const Node cn = nodes[cur];
               const double x_ = R.cpose[i][0], y_ = R.cpose[i][1], th = R.cpose[i][2];
 #ifdef AVP_NO_LOOKAHEAD
               found = htab_find(htab, hmask, nodes, x_, y_, th);
 #else
               found = R.found[i];
 #endif
-              const bool in_closed = found >= 0 && nodes[found].in_closed;
-              const bool oob = (s_nclosed > 0) && (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
-              skip = (in_closed || oob) ? 1 : 0;
+              in_closed = found >= 0 && nodes[found].in_closed;
+              oob_geo = (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
               coll = R.coll[i];
+            }
+            // closed_list is re-read for every successor (hybrid_a_star.py:155-163): while it is still empty (the root expansion) an
+            // earlier sibling that collides is appended to it (:202) and switches the boundary test on for the later ones.  The first
+            // such sibling cannot itself be skipped by the boundary test (nothing is closed before it), so it decides.
+            {
+              const unsigned appended = __ballot_sync(AVP_FULL_MASK, lane < nchild && !in_closed && found < 0 && coll);
+              const int first = appended ? (__ffs(appended) - 1) : 64;
+              const bool closed_nonempty = (s_nclosed > 0) || (first < lane);
+              skip = (in_closed || (oob_geo && closed_nonempty)) ? 1 : 0;
+            }
+            if (lane < nchild) {
+              const int i = lane;
+              const double th = R.cpose[i][2];
               const int need = (!skip) && ((found < 0 && !coll) || (found >= 0));
               const bool fwd = i < nchild / 2.0;
               double g = 0.0;
@@ -347,7 +401,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         } else if (lane == 0) {                  // prediction missed (or the very first pop): evaluate the popped node itself
           const Node &n = nodes[cur];
           EvalTarget T; T.valid = 1; T.node = cur; T.x = n.x; T.y = n.y; T.theta = n.theta; T.in_radius = n.in_radius; T.is_root = (cur == 0); T.shot = nshot[cur];
-          s_tgt = T; s_do_commit = 0; pc[6]++;
+          s_tgt = T; s_do_commit = 0; PROF(pc[6]++;)
         }
         // ---- the evaluators' queue for the target just published: counters, flags, header of the result buffer
         //      (the flags of the evaluation just finished were read above)
@@ -428,11 +482,9 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
                   Node &n = nodes[child];
                   const double f = s_g[i] + h;
                   n.h = h; n.f = f; n.in_open = 1;
-#ifdef AVP_NO_PROFILE
+                  PROF(const long long t_ = clock64();)
                   oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child);
-#else
-                  { const long long t_ = clock64(); oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child); pc[8] += clock64() - t_; pc[9]++; }
-#endif
+                  PROF(pc[8] += clock64() - t_; pc[9]++;)
                 } else {                                                    // :219-230 (in place, no re-heapify)
                   const double new_f = h + s_g[i];
                   if (new_f < s_oldf[i]) {
@@ -448,9 +500,9 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
             if (stop >= nchild) break;
             // heuristic miss for successor `stop`: Dijkstra.compute_path resumes (compute_h.py:198-214)
             long long term;
-            const long long td_ = clock64();
+            PROF(const long long td_ = clock64();)
             const int d = dij_compute_path(s_D, s_heap, R.cpose[stop][0], R.cpose[stop][1], &term);
-            if (lane == 0) { pc[10] += clock64() - td_; pc[11]++; }
+            PROF(if (lane == 0) { pc[10] += clock64() - td_; pc[11]++; })
             ++n_miss;
             if (lane == 0) {
               if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
@@ -504,7 +556,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
           if (lane == 0) it = atomicAdd(&s_work, 1);
           it = __shfl_sync(AVP_FULL_MASK, it, 0);
           if (it >= n_items) break;
-          const long long ti_ = clock64();
+          PROF(const long long ti_ = clock64();)
           if (it == 0) {
             int npts = 0;
             if (T.in_radius) {
@@ -660,7 +712,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
             }
             if (lane == 0) s_chit[i] = coll;
           }
-#ifndef AVP_NO_PROFILE
+#ifdef AVP_PROFILE
           if (lane == 0 && it < 40) atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[it]), (unsigned long long)(clock64() - ti_));
 #endif
         }
@@ -678,7 +730,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         const int n_sel = (nchild + 1) / 2;
         bool sel_left = true, chk_left = npts > 0;
         for (;;) {
-          const long long ti_ = clock64();
+          PROF(const long long ti_ = clock64();)
           int kind = -1, it = 0;                      // 0: selection, 1: course point
           // the choice must be the same on every lane (the branches contain shuffles): lane 0 reads the counter
           int rsd = 0;
@@ -719,7 +771,7 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
               W.shot[i] = w;
             }
           }
-#ifndef AVP_NO_PROFILE
+#ifdef AVP_PROFILE
           if (lane == 0) { const int k_ = 40 + kind; atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[k_]), (unsigned long long)(clock64() - ti_)); atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[k_ + 2]), 1ull); }
 #endif
         }
@@ -727,11 +779,32 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
       }
     }
     __syncthreads();
+#ifdef AVP_PROFILE
+    if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] += s_wp[warp][k]; }
+    if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_ic[tid];
+    if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] += pc[7]; o[12] += pc[12]; o[13] += pc[13]; { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); o[14] = ((long long)sm_ << 40) | (t_start & 0xffffffffffll); } o[15] += pc[15]; }
+    if (tid == 0 && P.prof) { long long *o = P.prof + (size_t)sc * 16; for (int k = 0; k < 7; ++k) o[k] += pc[k]; for (int k = 8; k < 12; ++k) o[k] += pc[k]; }
+#endif
+
+    if (s_status == AVP_PENDING) {
+      // ---- let go of the scenario: heap heads back to their save areas, counters to ScenState, the id to the tail of the run queue
+      for (int i = tid; i < s_D.hn && i < AVP_SM_HEAP; i += BLOCK) dgheap[i] = s_heap[i];
+      for (int i = tid; i < s_on && i < SMO; i += BLOCK) { int4 v; v.x = __double2loint(s_of[i]); v.y = __double2hiint(s_of[i]); v.z = s_oi[i]; v.w = 0; *reinterpret_cast<int4 *>(&oge[i]) = v; }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        ScenState st; st.phase = 1; st.slot = slot; st.status = 0; st.dij_hn = s_D.hn; st.dij_closed = s_D.closed_len;
+        st.nhq = s_nhq; st.nhcalls = s_nhcalls; st.G = s_G; st.nclosed = s_nclosed; st.npops = s_npops; st.on = s_on; st.cur = s_cur;
+        st.in_radius = s_in_radius; st.best_ok = s_best_ok; st.quanta = st0.quanta + 1; st.pad = 0;
+        PP.state[sc] = st;
+        atomicAdd(&ctl->n_suspends, 1);
+        ring_push(&ctl->q_tail, PP.queue, PP.q_mask, sc);
+      }
+      __syncthreads();
+      continue;
+    }
 
     // ---- finish: summary + finish_path (hybrid_a_star.py:351-389) + rs tail (path_planner.py:100-108)
-    if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] = s_wp[warp][k]; }
-    if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] = s_ic[tid];
-    if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] = pc[7]; o[12] = pc[12]; o[13] = pc[13]; { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); o[14] = ((long long)sm_ << 40) | (t_start & 0xffffffffffll); } o[15] = pc[15]; }     // o[14]: SM id and start clock (which scenarios shared a TPC, development aid)
     if (tid == 0) {
       avp_plan_summary &R = P.sums[sc];
       int status = s_status;
@@ -776,7 +849,10 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
         for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = rs_ct_names[b.ct][i];
       }
       if (dbg) dbg[0] = 9;
-      if (P.prof) { long long *o = P.prof + (size_t)sc * 16; for (int k = 0; k < 7; ++k) o[k] = pc[k]; for (int k = 8; k < 12; ++k) o[k] = pc[k]; }
+      PP.state[sc].phase = 2;
+      if (slot >= 0) ring_push(&ctl->slot_tail, PP.slot_ring, PP.slot_mask, slot);
+      __threadfence();
+      atomicAdd(&ctl->finalised, 1);
     }
     __syncthreads();
   }
@@ -785,7 +861,3 @@ __device__ __forceinline__ void search_pipe_body(const KParams &P) {
 #undef WP_ACC
 #undef TS
 }
-
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1) k_search_pipe(KParams P) { search_pipe_body<BLOCK>(P); }
-

@@ -213,3 +213,24 @@ def synthetic_set(n_maps: int, pairs_per_map: int, seed: int = 4, extent: float 
             out.append(s)
             k += 1
     return out
+
+
+def synthetic_candidates(n_maps: int, cand_per_map: int, seed: int = 4, extent: float = 20.0, n_poly: int = 256) -> List[List[Scenario]]:
+    """SURVEY §8d C4, batch-friendly: per map the obstacles and `cand_per_map` start/goal draws WITHOUT the collision rule (the
+    caller checks all candidates at once, e.g. on the GPU, and keeps the first free ones of every map).  One list per map."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for m in range(n_maps):
+        obs = synthetic_map_obstacles(rng, n_poly, extent)
+        lo, hi = 0.2 * extent, 0.8 * extent
+        cands = []
+        while len(cands) < cand_per_map:
+            p = rng.uniform(0.0, 1.0, size=6)
+            s = Scenario(float(lo + (hi - lo) * p[0]), float(lo + (hi - lo) * p[1]), float(-np.pi + 2 * np.pi * p[2]),
+                         float(lo + (hi - lo) * p[3]), float(lo + (hi - lo) * p[4]), float(-np.pi + 2 * np.pi * p[5]),
+                         obs, (0.0, extent, 0.0, extent), f"syn{m}_c{len(cands)}")
+            if np.hypot(s.x0 - s.xf, s.y0 - s.yf) < 1.0 or _axis_aligned(s.theta0) or _axis_aligned(s.thetaf):
+                continue
+            cands.append(s)
+        out.append(cands)
+    return out

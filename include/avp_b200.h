@@ -125,6 +125,11 @@ int avp_fetch_map(avp_ctx *ctx, int s, int32_t *dims, double *geom, uint8_t *cos
  * for m poses (x,y,theta triples) against scenario s's raster; out[m] = 0/1. */
 int avp_collision_check(avp_ctx *ctx, int s, int m, const double *poses, uint8_t *out);
 
+/* the same check at every loaded scenario's own start and goal pose (headings wrapped with pi_2_pi as in
+ * hybrid_a_star.py:105,109), one launch for the batch: out2n[2*s] = start collides, out2n[2*s+1] = goal collides.
+ * What the scenario recipes of BASELINE configs 2-4 need ("reject a draw if the checker reports a collision at start or goal"). */
+int avp_check_start_goal(avp_ctx *ctx, uint8_t *out2n);
+
 /* replaces the obstacle-raster scan of path_opti.compute_collision_H (optimization/path_optimazition.py:221-658)
  * and ocp_optimization.compute_collision_H (optimization/ocp_optimization.py:36-480) for m path points
  * (x,y,theta triples, theta in [-pi, pi]) of scenario s: out4[4*i..] = x_max, y_max, x_min, y_min, the free
@@ -192,9 +197,10 @@ int avp_dijkstra_query(avp_ctx *ctx, int s, int reset, double node_x, double nod
 int avp_timer_start(avp_ctx *ctx);
 int avp_timer_stop(avp_ctx *ctx, float *elapsed_ms);
 int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms);
-/* the search runs in two passes (narrow CTAs with a pop budget, then wide CTAs for the long
- * tail): per-pass CUDA-event times; n_pass2 = scenarios re-planned by pass 2 + 100000 * (pass-2 CTA width) */
-int avp_last_search_passes(avp_ctx *ctx, float *ms_pass1, float *ms_pass2, int32_t *n_pass2);
+/* the search is one eager-Dijkstra launch (one warp per scenario) and ONE persistent search launch with a round-robin run
+ * queue: their CUDA-event times; n_info = number of times a search let go of its SM at the end of a quantum
+ * (mod 100000) + 100000 * (CTA width of the search kernel) */
+int avp_last_search_passes(avp_ctx *ctx, float *ms_dijkstra, float *ms_search, int32_t *n_info);
 
 /* development aids: an in-kernel watchdog (SM clock cycles per scenario, 0 = off; a scenario
  * that exceeds it ends with AVP_CAPACITY) and the per-scenario progress checkpoints
