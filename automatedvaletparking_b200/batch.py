@@ -206,6 +206,30 @@ class DevicePlanner:
                                            _ip(pops) if pops is not None else None, cap_pops), "avp_fetch_results")
         return PlanResults(sums, paths, pops)
 
+    def split_paths(self, cap_pts: int = None, cap_seg: int = 32):
+        """PathPlanner.split_path (path_planner.py:112-192) for every finished plan of the last plan()/plan_resident(): one launch.
+        -> dict(status (n,), n_seg (n,), change_gear (n,), n_pts (n,), seg_len (n, cap_seg), pts (n, cap_pts, 3));
+        status: 0 ok, 1 no gear change (the reference raises IndexError), 2 the scenario has no path, 3 capacity."""
+        n = self.n
+        cap_pts = int(cap_pts or 768)
+        pts = np.zeros((n, cap_pts, 3)); seg = np.zeros((n, cap_seg), dtype=np.int32); info = np.zeros((n, 4), dtype=np.int32)
+        self._ck(self._L.avp_split_paths(self._h, cap_pts, cap_seg, _dp(pts), _ip(seg), _ip(info)), "avp_split_paths")
+        self.d2h_bytes += pts.nbytes + seg.nbytes + info.nbytes
+        return dict(status=info[:, 0].copy(), n_seg=info[:, 1].copy(), change_gear=info[:, 2].copy(), n_pts=info[:, 3].copy(), seg_len=seg, pts=pts)
+
+    def split_path(self, s: int, path, cap_seg: int = 64):
+        """PathPlanner.split_path(final_path) for one caller-supplied path against scenario s's raster
+        -> (status, list of segments as (len, 3) arrays, change_gear)"""
+        p = np.ascontiguousarray(np.asarray(path, dtype=np.float64).reshape(-1, 3))
+        cap_pts = len(p) + cap_seg * (1 + 2 * int(self.cfg.extended_num)) + 8
+        pts = np.zeros((cap_pts, 3)); seg = np.zeros(cap_seg, dtype=np.int32); info = np.zeros(4, dtype=np.int32)
+        self._ck(self._L.avp_split_path(self._h, s, len(p), _dp(p), cap_pts, cap_seg, _dp(pts), _ip(seg), _ip(info)), "avp_split_path")
+        st, ns, cg, npt = (int(v) for v in info)
+        segs, o = [], 0
+        for k in range(min(ns, cap_seg)):
+            segs.append(pts[o:o + int(seg[k])].copy()); o += int(seg[k])
+        return st, segs, cg
+
     def result_device_pointers(self):
         s, p = ctypes.c_void_p(), ctypes.c_void_p()
         n, cp = ctypes.c_int64(), ctypes.c_int64()

@@ -378,7 +378,7 @@ static int ensure_ws(avp_ctx *ctx, int ctas) {
   size_t fit = (size_t)((double)free_b * 0.8) / slot_bytes;
   { const char *se = getenv("AVP_SLOTS"); if (se && atoi(se) > 0) fit = (size_t)atoi(se); }      // development aid: force the slot pool to run dry
   int slots = n; if ((size_t)slots > fit) slots = (int)fit;
-  if (slots < ctas + 1 && slots < n) FAIL("plan: not enough device memory for the search workspaces");
+  if (slots < 1) FAIL("plan: not enough device memory for the search workspaces");
   CK(cudaMalloc(&ctx->d_nodes, sizeof(Node) * (size_t)slots * node_cap));
   CK(cudaMalloc(&ctx->d_nshot, sizeof(NodeShot) * (size_t)slots * node_cap));
   CK(cudaMalloc(&ctx->d_oheap, sizeof(OEnt) * (size_t)slots * node_cap));
@@ -537,6 +537,46 @@ extern "C" int avp_result_device_buffer(avp_ctx *ctx, void **sums, void **paths,
   if (!ctx) return -3;
   if (ctx->res_n != ctx->n || !ctx->d_sums) FAIL("avp_result_device_buffer: no results");
   if (sums) *sums = ctx->d_sums; if (paths) *paths = ctx->d_paths; if (n) *n = ctx->n; if (cap_path) *cap_path = ctx->cap_path;
+  return 0;
+}
+
+extern "C" int avp_split_paths(avp_ctx *ctx, int cap_pts, int cap_seg, double *split_pts, int32_t *seg_len, int32_t *info) {
+  if (!ctx) return -3;
+  if (ctx->res_n != ctx->n || !ctx->d_sums) FAIL("avp_split_paths: no plan results on the device (call avp_plan_batch first)");
+  if (cap_pts <= 0 || cap_seg <= 0 || !split_pts || !seg_len || !info) FAIL("avp_split_paths: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n;
+  const size_t b_pts = sizeof(double) * n * cap_pts * 3, b_seg = sizeof(int32_t) * n * cap_seg, b_inf = sizeof(int32_t) * n * 4;
+  if (ensure_scratch(ctx, b_pts + b_seg + b_inf + 64)) return -1;
+  double *d_pts = (double *)ctx->d_scratch; int32_t *d_seg = (int32_t *)((char *)ctx->d_scratch + b_pts), *d_inf = (int32_t *)((char *)ctx->d_scratch + b_pts + b_seg);
+  CK(cudaMemsetAsync(d_seg, 0, b_seg, ctx->stream));
+  k_split_batch<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(ctx->cfg, ctx->d_scen, (int)n, ctx->d_cells, ctx->d_col, ctx->d_sums, ctx->d_paths, ctx->cap_path,
+                                                               d_pts, cap_pts, d_seg, cap_seg, d_inf); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(split_pts, d_pts, b_pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(seg_len, d_seg, b_seg, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(info, d_inf, b_inf, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int avp_split_path(avp_ctx *ctx, int s, int n_pts, const double *path, int cap_pts, int cap_seg, double *split_pts, int32_t *seg_len, int32_t *info4) {
+  if (!ctx) return -3;
+  if (s < 0 || s >= ctx->n || n_pts < 0 || cap_pts <= 0 || cap_seg <= 0 || !split_pts || !seg_len || !info4 || (n_pts > 0 && !path)) FAIL("avp_split_path: bad arguments");
+  if (!ctx->rasterised) FAIL("avp_split_path: call avp_rasterise first");
+  CK(cudaSetDevice(ctx->device));
+  const size_t b_in = sizeof(double) * 3 * (size_t)(n_pts > 0 ? n_pts : 1), b_pts = sizeof(double) * 3 * (size_t)cap_pts, b_seg = sizeof(int32_t) * (size_t)cap_seg;
+  if (ensure_scratch(ctx, b_in + b_pts + b_seg + 16 + 64)) return -1;
+  double *d_in = (double *)ctx->d_scratch, *d_pts = (double *)((char *)ctx->d_scratch + b_in);
+  int32_t *d_seg = (int32_t *)((char *)ctx->d_scratch + b_in + b_pts), *d_inf = (int32_t *)((char *)ctx->d_scratch + b_in + b_pts + b_seg);
+  if (n_pts > 0) CK(cudaMemcpyAsync(d_in, path, sizeof(double) * 3 * (size_t)n_pts, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_seg, 0, b_seg, ctx->stream));
+  k_split_one<<<1, 32, 0, ctx->stream>>>(ctx->cfg, ctx->d_scen, s, ctx->d_cells, ctx->d_col, d_in, n_pts, d_pts, cap_pts, d_seg, cap_seg, d_inf); ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(split_pts, d_pts, b_pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(seg_len, d_seg, b_seg, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(info4, d_inf, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

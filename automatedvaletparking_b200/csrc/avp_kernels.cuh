@@ -206,6 +206,101 @@ __global__ void __launch_bounds__(128) k_check_start_goal(avp_config cfg, const 
   if ((threadIdx.x & 31) == 0) out[w] = hit ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// PathPlanner.split_path (path_planner.py:112-192), SURVEY 8f row 1: gear-change detection and collision-checked
+// extension points.  One warp per path.  Gear change at i  <=>  1 - scipy.spatial.distance.cosine(v1, v2) < 0 with
+// v1 = p[i+1] - p[i], v2 = p[i+2] - p[i+1]  (:126-136); scipy 1.18 evaluates  dist = 1.0 - uv / sqrt(uu * vv)  with
+// np.dot (2-element ddot: fma(a1, b1, a0 * b0), pinned by tests/golden/leaf_split.npz), clips it to [0, 2], and a zero
+// displacement gives NaN (no gear change).  The lanes evaluate 32 consecutive i at once; the changes are then handled in
+// order: segment k = [the previous change's accepted extension points, last first (:141-147)] + rows start..i+1 +
+// [up to extended_num points rolled forward from p[i+1] with the gear of step i, each kept only if collision free
+// (:150-174)].  Output: the segments back to back (= out_final_path of path_planning, :52) and their lengths.
+// info[4] = status, number of segments, change_gear, number of points.
+enum { AVP_SPLIT_OK = 0, AVP_SPLIT_NO_GEAR_CHANGE = 1 /* reference: IndexError at :181 */, AVP_SPLIT_NO_PATH = 2, AVP_SPLIT_CAPACITY = 3 };
+#define AVP_EXT_MAX 8
+
+__device__ __forceinline__ bool split_gear_change(const double *p, int i) {
+  const double u0 = p[3 * (i + 1)] - p[3 * i], u1 = p[3 * (i + 1) + 1] - p[3 * i + 1];
+  const double v0 = p[3 * (i + 2)] - p[3 * (i + 1)], v1 = p[3 * (i + 2) + 1] - p[3 * (i + 1) + 1];
+  const double uv = __fma_rn(u1, v1, u0 * v0), uu = __fma_rn(u1, u1, u0 * u0), vv = __fma_rn(v1, v1, v0 * v0);
+  double dist = 1.0 - uv / sqrt(uu * vv);
+  if (dist < 0.0) dist = 0.0; else if (dist > 2.0) dist = 2.0;      // np.clip (NaN stays NaN)
+  return (1 - dist) < 0;
+}
+
+__device__ __forceinline__ void split_path_warp(const avp_config &cfg, const ScenDev &S, const double2 *cells, const int32_t *col_start,
+                                                const double *p, int nf, double *out, int cap_pts, int32_t *seg_len, int cap_seg, int32_t *info) {
+  const int lane = threadIdx.x & 31;
+  int start = 0, change = 0, have = 0, nseg = 0, npts = 0; bool over = false;
+  double ext[AVP_EXT_MAX][3];                       // accepted extension points of the latest gear change (same values on every lane)
+  const int next = cfg.extended_num < AVP_EXT_MAX ? cfg.extended_num : AVP_EXT_MAX;
+  auto put = [&](int at, double x, double y, double t) { if (at < cap_pts) { out[3 * at] = x; out[3 * at + 1] = y; out[3 * at + 2] = t; } else over = true; };
+  for (int base = 0; base < nf - 2; base += 32) {
+    const int ii = base + lane;
+    unsigned m = __ballot_sync(AVP_FULL_MASK, ii < nf - 2 && split_gear_change(p, ii));
+    while (m) {
+      const int i = base + __ffs(m) - 1; m &= m - 1;
+      change++;
+      const int end = i + 2;
+      int pre = 0;
+      if (change > 1 && have > 0) {                 // :141-147: insert(0, ...) one by one reverses their order
+        for (int j = 0; j < have; ++j) if (lane == 0) put(npts + j, ext[have - 1 - j][0], ext[have - 1 - j][1], ext[have - 1 - j][2]);
+        pre = have; have = 0;
+      }
+      for (int r = lane; r < end - start; r += 32) put(npts + pre + r, p[3 * (start + r)], p[3 * (start + r) + 1], p[3 * (start + r) + 2]);
+      int len = pre + (end - start);
+      for (int j = 0; j < next; ++j) {              // :150-174
+        const double xi = p[3 * i], thi = p[3 * i + 2], xn = p[3 * (i + 1)], yn = p[3 * (i + 1) + 1], thn = p[3 * (i + 1) + 2];
+        const bool f1 = (xn > xi) && (thi > -AVP_PI / 2 && thi < AVP_PI / 2);
+        const bool f2 = (xn < xi) && ((thi > AVP_PI / 2 && thi < AVP_PI) || (thi > -AVP_PI && thi < -AVP_PI / 2));
+        const double speed = (f1 || f2) ? cfg.max_v : -cfg.max_v;
+        const double td = speed * cfg.ddt * (j + 1);
+        const double cs = d_cos(thn), sn = d_sin(thn);
+        const double xj = xn + td * cs, yj = yn + td * sn;
+        if (!check_pose_cs_warp(cfg, S, cells, col_start, xj, yj, cs, sn)) {
+          if (lane == 0) put(npts + len, xj, yj, thn);
+          ext[have][0] = xj; ext[have][1] = yj; ext[have][2] = thn; ++have; ++len;
+        }
+      }
+      if (lane == 0) { if (nseg < cap_seg) seg_len[nseg] = len; else over = true; }
+      ++nseg; npts += len; start = i + 1;
+    }
+  }
+  int status = AVP_SPLIT_OK;
+  if (nseg == 0) status = AVP_SPLIT_NO_GEAR_CHANGE;            // :181 pre_path = split_path[-1] on an empty list
+  else {
+    int pre = 0;
+    if (have > 0) { for (int j = 0; j < have; ++j) if (lane == 0) put(npts + j, ext[have - 1 - j][0], ext[have - 1 - j][1], ext[have - 1 - j][2]); pre = have; }
+    for (int r = lane; r < nf - start; r += 32) put(npts + pre + r, p[3 * (start + r)], p[3 * (start + r) + 1], p[3 * (start + r) + 2]);
+    const int len = pre + (nf - start);
+    if (lane == 0) { if (nseg < cap_seg) seg_len[nseg] = len; else over = true; }
+    ++nseg; npts += len;
+  }
+  if (__any_sync(AVP_FULL_MASK, over)) status = AVP_SPLIT_CAPACITY;
+  if (lane == 0) { info[0] = status; info[1] = nseg; info[2] = change; info[3] = npts; }
+}
+
+// every finished plan of the batch (results resident on the device), one warp per scenario
+__global__ void __launch_bounds__(128) k_split_batch(avp_config cfg, const ScenDev *scen, int n, const double2 *cells, const int32_t *col_start,
+                                                     const avp_plan_summary *sums, const double *paths, int cap_path,
+                                                     double *out, int cap_pts, int32_t *seg_len, int cap_seg, int32_t *info) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n) return;
+  const int lane = threadIdx.x & 31;
+  int32_t *inf = info + 4 * (size_t)w;
+  if (sums[w].status != AVP_OK) { if (lane == 0) { inf[0] = AVP_SPLIT_NO_PATH; inf[1] = 0; inf[2] = 0; inf[3] = 0; } return; }
+  if (sums[w].n_final > cap_path) { if (lane == 0) { inf[0] = AVP_SPLIT_CAPACITY; inf[1] = 0; inf[2] = 0; inf[3] = 0; } return; }
+  const ScenDev &S = scen[w];
+  split_path_warp(cfg, S, cells + S.cell_off, col_start + S.col_off, paths + (size_t)w * cap_path * 3, sums[w].n_final,
+                  out + (size_t)w * cap_pts * 3, cap_pts, seg_len + (size_t)w * cap_seg, cap_seg, inf);
+}
+// one caller-supplied path against scenario s's raster (the drop-in PathPlanner.split_path)
+__global__ void __launch_bounds__(32) k_split_one(avp_config cfg, const ScenDev *scen, int s, const double2 *cells, const int32_t *col_start,
+                                                  const double *path, int nf, double *out, int cap_pts, int32_t *seg_len, int cap_seg, int32_t *info) {
+  const ScenDev &S = scen[s];
+  split_path_warp(cfg, S, cells + S.cell_off, col_start + S.col_off, path, nf, out, cap_pts, seg_len, cap_seg, info);
+}
+
 // Corridor extraction: path_opti.compute_collision_H (optimization/path_optimazition.py:221-658)
 // and its copy ocp_optimization.compute_collision_H (optimization/ocp_optimization.py:36-480).
 // One warp per path point; the lanes scan the obstacle cells of the raster columns covered by the AABB of the

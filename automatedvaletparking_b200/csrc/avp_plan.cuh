@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
   __shared__ int s_trace_on;
   __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts)
   __shared__ long long s_wp[BLOCK / 32][8];   // per warp: cycles lane 0 spent working in each evaluator phase (barrier waits excluded)
+  __shared__ long long s_subt[16];            // thread 0: sub-intervals of the serial section between barriers A and B
 #endif
 
   const avp_config &cfg = P.cfg;
@@ -225,6 +226,9 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
 #define WP_ACC(k) do { if (lane == 0) { const long long t_ = clock_ordered(); s_wp[warp][k] += t_ - wt; wt = t_; } } while (0)
     if (lane == 0) for (int k = 0; k < 8; ++k) s_wp[warp][k] = 0;
     if (tid < 48) s_ic[tid] = 0;
+    if (tid < 16) s_subt[tid] = 0;
+    long long st_ = 0;
+#define SUBT(k) do { if (tid == 0) { const long long t_ = clock_ordered(); s_subt[k] += t_ - st_; st_ = t_; } } while (0)
     long long *tsw = (P.wprof && warp < 16) ? P.wprof + ((size_t)sc * 16 + warp) * 24 + 8 : nullptr;
 #define TS(k) do { __syncwarp(); if (lane == 0 && tsw && ((k) < 2 ? (s_npops == P.trace_pop) : s_trace_on)) tsw[k] = clock_ordered(); } while (0)
 #else
@@ -232,6 +236,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
 #define WP_START() do { } while (0)
 #define WP_ACC(k) do { } while (0)
 #define TS(k) do { } while (0)
+#define SUBT(k) do { } while (0)
 #endif
 
     // open_list.get() (path_planner.py:70) with the loop's exit tests; lane 0 of the commit warp
@@ -305,22 +310,26 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
     for (;;) {
       __syncthreads();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
       PIPE_TICK(0, 4);                           // commit warp waiting for the evaluators
+      PROF(if (tid == 0) st_ = clock_ordered();)
       TS(0);
       // s_ctlA is written by do_pop (between B and A) and read here; s_ctlB is written between A and B and read
       // after B: no control word is written while another warp may still be reading it
       if (s_ctlA == CTL_EXIT) break;
       if (warp == 0) {
+        SUBT(0);
         WP_START();
         const int wb = s_rb ^ 1;
         const int cur = s_cur;
         if (lane == 0) { s_ctlB = CTL_RUN; PROF(s_trace_on = (s_npops == P.trace_pop);) }
         __syncwarp();
+        SUBT(1);
         if (s_res[wb].node == cur) {             // the result of the popped node is there
           PureRes &R = s_res[wb];
           const int shot_bad = R.in_radius ? s_shot_bad : 0, shot_coll = R.in_radius ? s_shot_coll : 0;   // of the evaluation just finished
           if (lane < nchild) R.coll[lane] = s_chit[lane];          // sub-step collision flags of the evaluation just finished
           if (lane == 0) { s_rb = wb; s_in_radius = R.in_radius; s_best_ok = R.shot_ok; PROF(pc[5]++;) }
           __syncwarp();
+          SUBT(2);
           if (shot_bad) { if (lane == 0) { s_status = (shot_bad == 1) ? AVP_RS_DEGENERATE : AVP_CAPACITY; s_ctlB = CTL_EXIT; } }
           else if (R.in_radius && !shot_coll) { if (lane == 0) s_ctlB = CTL_FINISH; }     // path_planner.py:86-88
           else {
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
               oob_geo = (x_ > S.b[1] || x_ < S.b[0] || y_ > S.b[3] || y_ < S.b[2]);
               coll = R.coll[i];
             }
+            SUBT(3);
             // closed_list is re-read for every successor (hybrid_a_star.py:155-163): while it is still empty (the root expansion) an
             // earlier sibling that collides is appended to it (:202) and switches the boundary test on for the later ones.  The first
             // such sibling cannot itself be skipped by the boundary test (nothing is closed before it), so it decides.
@@ -371,6 +381,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
               s_h1[i] = s_hv[i] / 100.0;                                  // h_value_1 / 100 (:295)
             }
             __syncwarp();
+            SUBT(4);
             // ---- predict the next open_list.get(): the pushes of this commit put a successor at the root iff its f is
             //      below the root's; among successors the first one with the smallest f wins (heapq._siftdown is strict)
             double fc = INFINITY;
@@ -384,6 +395,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
               const double of_ = shfl_d(fc, lane ^ o); const int oi_ = __shfl_xor_sync(AVP_FULL_MASK, bi, o);
               if (of_ < fc || (of_ == fc && oi_ < bi)) { fc = of_; bi = oi_; }
             }
+            SUBT(5);
             if (lane == 0) {
               EvalTarget T; T.valid = 0; T.node = -1; T.is_root = 0; T.in_radius = 0; T.x = 0.0; T.y = 0.0; T.theta = 0.0;
               T.shot.t = 0.0; T.shot.u = 0.0; T.shot.v = 0.0; T.shot.L = 0.0; T.shot.inst = -1; T.shot.ok = 0;
@@ -406,6 +418,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
         // ---- the evaluators' queue for the target just published: counters, flags, header of the result buffer
         //      (the flags of the evaluation just finished were read above)
         __syncwarp();
+        SUBT(6);
         if (s_ctlB == CTL_RUN) {
           if (lane < nchild) { s_valid[lane] = 0ull; s_chit[lane] = 0; }
           if (lane == 0) {
@@ -416,8 +429,9 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
           }
         }
       }
-      if (warp == 0) WP_ACC(0);
+      if (warp == 0) { SUBT(7); WP_ACC(0); }
       PIPE_TICK(0, 1);                           // accept + lookups + prediction
+      SUBT(8);
       TS(1);
       __syncthreads();                                 // ---- barrier B: target published
       TS(2);
@@ -782,6 +796,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
 #ifdef AVP_PROFILE
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] += s_wp[warp][k]; }
     if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_ic[tid];
+    if (tid < 16 && P.wprof) P.wprof[((size_t)sc * 16 + 8 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_subt[tid];
     if (tid == 32 && P.prof) { long long *o = P.prof + (size_t)sc * 16; o[7] += pc[7]; o[12] += pc[12]; o[13] += pc[13]; { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); o[14] = ((long long)sm_ << 40) | (t_start & 0xffffffffffll); } o[15] += pc[15]; }
     if (tid == 0 && P.prof) { long long *o = P.prof + (size_t)sc * 16; for (int k = 0; k < 7; ++k) o[k] += pc[k]; for (int k = 8; k < 12; ++k) o[k] += pc[k]; }
 #endif
@@ -860,4 +875,5 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
 #undef WP_START
 #undef WP_ACC
 #undef TS
+#undef SUBT
 }

@@ -3,7 +3,7 @@
 a_star_plan() runs the WHOLE search on the GPU (avp_plan_batch: raster, lazy Dijkstra heuristic,
 successor expansion, rs shots) and returns the reference's tuple (final_path, astar_path, PATH);
 path_planning() adds split_path (gear-change splitting with collision-checked extension points,
-path_planner.py:112-192; its checks run on the GPU).  A search the reference cannot finish raises
+path_planner.py:112-192), also computed on the device (avp_split_path).  A search the reference cannot finish raises
 the same exception class the reference raises (AttributeError for an exhausted open list)."""
 import copy
 from typing import Dict, List, Tuple
@@ -107,47 +107,14 @@ class PathPlanner:
         return final_path, a_star_path, rs_path
 
     def split_path(self, final_path: List[List]) -> Tuple[List[List[List]], int]:
-        """path_planner.py:112-192"""
-        from scipy import spatial
-        split_path = []
-        change_gear = 0
-        start = 0
-        extend_num = self.config['extended_num']
-        have_extended_points = 0
-        ddt = self.config['trajectory_dt']
-        for i in range(len(final_path) - 2):
-            vector_1 = (final_path[i + 1][0] - final_path[i][0], final_path[i + 1][1] - final_path[i][1])
-            vector_2 = (final_path[i + 2][0] - final_path[i + 1][0], final_path[i + 2][1] - final_path[i + 1][1])
-            compute_cosin = 1 - spatial.distance.cosine(vector_1, vector_2)
-            if compute_cosin < 0:
-                change_gear += 1
-                end = i + 2
-                input_path = final_path[start:end]
-                if change_gear > 1 and have_extended_points > 0:
-                    pre_path = split_path[-1]
-                    for j in range(have_extended_points):
-                        p = pre_path[-(have_extended_points - j)]
-                        input_path.insert(0, [p[0], p[1], p[2]])
-                    have_extended_points = 0
-                for j in range(extend_num):
-                    th_i = final_path[i][2]
-                    forward_1 = (final_path[i + 1][0] > final_path[i][0]) and (-np.pi / 2 < th_i < np.pi / 2)
-                    forward_2 = (final_path[i + 1][0] < final_path[i][0]) and ((np.pi / 2 < th_i < np.pi) or (-np.pi < th_i < -np.pi / 2))
-                    speed = self.vehicle.max_v if (forward_1 or forward_2) else -self.vehicle.max_v
-                    td_j = speed * ddt * (j + 1)
-                    theta_j = final_path[i + 1][2]
-                    x_j = final_path[i + 1][0] + td_j * np.cos(theta_j)
-                    y_j = final_path[i + 1][1] + td_j * np.sin(theta_j)
-                    if not self.collision_checker.check(node_x=x_j, node_y=y_j, theta=theta_j):
-                        input_path.append([x_j, y_j, theta_j])
-                        have_extended_points += 1
-                split_path.append(input_path)
-                start = i + 1
-        input_path = final_path[start:]
-        pre_path = split_path[-1]
-        if have_extended_points > 0:
-            for j in range(have_extended_points):
-                p = pre_path[-(have_extended_points - j)]
-                input_path.insert(0, [p[0], p[1], p[2]])
-        split_path.append(input_path)
-        return split_path, int(change_gear)
+        """path_planner.py:112-192 on the device (avp_split_path: gear-change detection with scipy's cosine semantics, collision-checked
+        extension points, segment assembly); returns the reference's (split_path_list, change_gear).  A path without a gear
+        change raises IndexError as the reference does (:181, split_path[-1] on an empty list)."""
+        dev = self.collision_checker._device()           # the context whose config / vehicle / inflation the checker uses
+        status, segs, change_gear = dev.split_path(0, final_path)
+        if status == 1:
+            raise IndexError("list index out of range")
+        if status != 0:
+            raise RuntimeError(f"split_path: device status {status}")
+        split = [[[float(r[0]), float(r[1]), float(r[2])] for r in seg] for seg in segs]
+        return split, int(change_gear)

@@ -49,7 +49,9 @@ STATUS = {0: "ok", 1: "open_exhausted", 2: "open_exhausted_rs", 3: "h_unreachabl
 WORKLOAD_TEXT = {
     "c2": "Case1 obstacle map, 1024 randomised start/goal poses per GPU (BASELINE configs[1], SURVEY 8d C2)",
     "c3": "all 20 BenchmarkCases x 256 perturbed start/goal poses = 5120 scenarios, sharded over the GPUs (BASELINE configs[2], SURVEY 8d C3)",
-    "c4": "64 synthetic 200x200 maps x 256 convex polygons x 64 start/goal pairs = 4096 scenarios, sharded over the GPUs (BASELINE configs[3], SURVEY 8d C4)",
+    "c4": "64 synthetic 200x200 maps x 256 convex polygons x 64 start/goal pairs = 4096 scenarios, sharded over the GPUs (BASELINE configs[3], SURVEY 8d C4); "
+          "at this obstacle density no pose is collision free, every search ends at its first pop: the step is rasterisation + eager Dijkstra",
+    "c4s": "as c4 with 24 polygons per map and collision-free start/goal poses (searches that run): 4096 scenarios, sharded over the GPUs",
 }
 
 
@@ -60,43 +62,46 @@ def make_candidates(rank: int, n: int = N_SCEN):
     return scn.perturbed_candidates(scn.benchmark_case(1), 8 * n, seed=1 + 1000 * rank)
 
 
-def _collisions(cands, dp, cfg=None):
-    """start / goal collision flags of every candidate: on the GPU (the product's own checker, one launch) when a
-    DevicePlanner is given, else on the oracle (the reference arm; both agree bit for bit, tests/test_gpu_parity.py)."""
-    if dp is not None:
-        dp.load(cands)
-        return dp.start_goal_collisions()
-    import oracle_lib as O
-    from automatedvaletparking_b200.batch import _pi_2_pi
-    a, b = [], []
-    for s in cands:
-        m = O.OracleMap(s)
-        a.append(m.check(cfg, s.x0, s.y0, _pi_2_pi(s.theta0)))
-        b.append(m.check(cfg, s.xf, s.yf, _pi_2_pi(s.thetaf)))
-    return np.array(a, dtype=bool), np.array(b, dtype=bool)
+def _collisions(cands, dp, cfg=None, need=None):
+    """start / goal collision flags of the candidates: on the GPU (the product's own checker, one launch per 4096 candidates)
+    when a DevicePlanner is given, else on the oracle (the reference arm; both agree bit for bit, tests/test_gpu_parity.py).
+    With `need`, stops after the chunk in which the need-th collision-free candidate was seen; returns flags for the
+    candidates looked at (a prefix)."""
+    a, b, free = [], [], 0
+    chunk = 4096 if dp is not None else 64               # bounded uploads: every candidate gets its own raster and h-table space
+    if dp is None:
+        import oracle_lib as O
+        from automatedvaletparking_b200.batch import _pi_2_pi
+    for k in range(0, len(cands), chunk):
+        part = cands[k:k + chunk]
+        if dp is not None:
+            dp.load(part)
+            ak, bk = dp.start_goal_collisions()
+        else:
+            ak, bk = np.zeros(len(part), dtype=bool), np.zeros(len(part), dtype=bool)
+            for i, s in enumerate(part):
+                m = O.OracleMap(s)
+                ak[i] = m.check(cfg, s.x0, s.y0, _pi_2_pi(s.theta0))
+                bk[i] = m.check(cfg, s.xf, s.yf, _pi_2_pi(s.thetaf))
+        a.append(ak); b.append(bk)
+        free += int((~(ak | bk)).sum())
+        if need is not None and free >= need:
+            break
+    return np.concatenate(a), np.concatenate(b)
 
 
 def make_scenarios(rank: int, n: int = N_SCEN, dp=None):
     """SURVEY 8d C2 recipe incl. the rule that start and goal poses are collision free."""
     from automatedvaletparking_b200 import scenarios as scn
+    from automatedvaletparking_b200.hostcfg import make_avp_config
     cands = make_candidates(rank, n)
-    if dp is not None:
-        a, b = _collisions(cands, dp)
-    else:
-        from automatedvaletparking_b200.hostcfg import make_avp_config
-        cfg = make_avp_config()
-        a, b = [], []
-        for k in range(0, len(cands), 64):              # the oracle is serial: stop as soon as n free candidates are known
-            ak, bk = _collisions(cands[k:k + 64], None, cfg)
-            a += list(ak); b += list(bk)
-            if len(a) - sum(x or y for x, y in zip(a, b)) >= n:
-                break
-        cands = cands[:len(a)]
-    return scn.keep_collision_free(cands, a, b, n)
+    a, b = _collisions(cands, dp, make_avp_config(), need=n)
+    return scn.keep_collision_free(cands[:len(a)], a, b, n)
 
 
 def make_c3(dp=None, per_case: int = 256, cases=range(1, 21)):
-    """for each case `per_case` perturbations (seed 100 + case) with the C2 recipe incl. the collision rule."""
+    """for each case `per_case` perturbations (seed 100 + case) with the C2 recipe incl. the collision rule: the first
+    `per_case` collision-free draws of the case's seeded stream (Case8 accepts 0.3 % of the draws, Case20's base start pose collides)."""
     from automatedvaletparking_b200 import scenarios as scn
     from automatedvaletparking_b200.hostcfg import make_avp_config
     cfg = make_avp_config()
@@ -105,37 +110,38 @@ def make_c3(dp=None, per_case: int = 256, cases=range(1, 21)):
         base = scn.benchmark_case(c)
         over = 8
         while True:
-            cands = scn.perturbed_candidates(base, over * per_case, seed=100 + c)
-            if dp is None and per_case <= 8:
-                cands = cands[:64 * per_case]
-            a, b = _collisions(cands, dp, cfg)
+            cands = scn.perturbed_candidates(base, over * per_case, seed=100 + c)      # a longer draw of the same stream: same prefix
+            a, b = _collisions(cands, dp, cfg, need=per_case)
             free = [s for s, x, y in zip(cands, a, b) if not (x or y)]
-            if len(free) >= per_case or over >= 64:
+            if len(free) >= per_case or over >= 4096:
                 break
-            over *= 4                                    # a cluttered case (Case20's base start pose collides): draw more
+            over *= 8
         if len(free) < per_case:
             raise RuntimeError(f"Case{c}: only {len(free)} collision-free perturbations")
         out += free[:per_case]
     return out
 
 
-def make_c4(dp=None, n_maps: int = 64, pairs: int = 64):
-    """synthetic maps (seed 4), per map the first `pairs` collision-free of 4*pairs start/goal draws."""
+def make_c4(dp=None, n_maps: int = 64, pairs: int = 64, n_poly: int = 256, collision_free: bool = False):
+    """synthetic 200x200 maps (seed 4) with `n_poly` convex polygons, `pairs` start/goal draws per map.
+    With 256 polygons NO pose of the 4.9 m x 2.1 m inflated footprint is collision free (0 of 4000 random poses, oracle), so the
+    collision rule of the recipe cannot be applied: the draws are taken as they come and every search ends at its first pop
+    (status parity; the step is rasterisation + eager Dijkstra).  `collision_free=True` (used with fewer polygons: c4s) keeps
+    the first `pairs` collision-free of 64*pairs draws per map."""
     from automatedvaletparking_b200 import scenarios as scn
     from automatedvaletparking_b200.hostcfg import make_avp_config
+    if not collision_free:
+        return scn.synthetic_set(n_maps, pairs, seed=4, n_poly=n_poly)
     cfg = make_avp_config()
-    maps = scn.synthetic_candidates(n_maps, 4 * pairs, seed=4)
-    flat = [s for m in maps for s in m]
+    per = 64 * pairs
+    maps = scn.synthetic_candidates(n_maps, per, seed=4, n_poly=n_poly)
     out = []
-    chunk = 64 * 4 * pairs                               # 64 maps of candidates per upload
-    for k in range(0, len(flat), chunk):
-        part = flat[k:k + chunk]
-        a, b = _collisions(part, dp, cfg)
-        for m0 in range(0, len(part), 4 * pairs):
-            free = [s for s, x, y in zip(part[m0:m0 + 4 * pairs], a[m0:m0 + 4 * pairs], b[m0:m0 + 4 * pairs]) if not (x or y)]
-            if len(free) < pairs:
-                raise RuntimeError("synthetic map too cluttered")
-            out += free[:pairs]
+    for m in maps:
+        a, b = _collisions(m, dp, cfg, need=pairs)
+        free = [s for s, x, y in zip(m, a, b) if not (x or y)]
+        if len(free) < pairs:
+            raise RuntimeError(f"synthetic map: only {len(free)} of {per} draws are collision free")
+        out += free[:pairs]
     return out
 
 
@@ -145,7 +151,7 @@ def make_workload(name: str, rank: int, world: int, dp, n_c2: int = N_SCEN):
     if name == "c2":
         scs = make_scenarios(rank, n_c2, dp)
         return scs, n_c2 * world, "weak", np.arange(rank * n_c2, (rank + 1) * n_c2)
-    full = make_c3(dp) if name == "c3" else make_c4(dp)
+    full = make_c3(dp) if name == "c3" else make_c4(dp) if name == "c4" else make_c4(dp, n_poly=24, collision_free=True)
     keys = [avd.cost_proxy(s) for s in full]
     idx = avd.shard_indices(len(full), rank, world, keys)
     return [full[i] for i in idx], len(full), "strong", idx
@@ -472,7 +478,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c4s"])
     ap.add_argument("--scenarios", type=int, default=N_SCEN, help="c2 only: scenarios per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other workloads and the Case1 latency")

@@ -192,6 +192,16 @@ int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *
  * avp_fetch_hvalues.  A plan run reuses the per-id arrays and invalidates this state. */
 int avp_dijkstra_query(avp_ctx *ctx, int s, int reset, double node_x, double node_y, int32_t *dist, int32_t *closed_len, int32_t *target_id);
 
+/* replaces PathPlanner.split_path (path_planner.py:112-192): gear-change detection (scipy.spatial.distance.cosine semantics,
+ * NaN for a zero displacement) and the collision-checked extension points, for every finished plan of the batch (results of
+ * the last avp_plan_batch, still on the device), one launch.  Per scenario: split_pts[cap_pts][3] = the segments back to back
+ * (= out_final_path of path_planning, :52), seg_len[cap_seg] = their lengths (split_path_list), info[4] = {status, number of
+ * segments, change_gear, number of points}.  status: 0 ok; 1 the path has no gear change (the reference raises IndexError at
+ * :181); 2 the scenario has no path (plan status != AVP_OK); 3 cap_pts / cap_seg / the plan's cap_path too small. */
+int avp_split_paths(avp_ctx *ctx, int cap_pts, int cap_seg, double *split_pts, int32_t *seg_len, int32_t *info);
+/* the same for ONE caller-supplied path (n_pts rows x, y, theta) against scenario s's raster: PathPlanner.split_path(final_path) */
+int avp_split_path(avp_ctx *ctx, int s, int n_pts, const double *path, int cap_pts, int cap_seg, double *split_pts, int32_t *seg_len, int32_t *info4);
+
 /* CUDA-event stopwatch on the context's stream around any sequence of entry points, and the
  * CUDA-event duration of the most recent search-kernel launch (bench.py timing legs) */
 int avp_timer_start(avp_ctx *ctx);

@@ -1012,3 +1012,60 @@ void orc_expand_pure(const orc_map *m, const avp_config *c, const double parent[
 
 double orc_py_hypot(double a, double b) { return py_hypot(a, b); }
 double orc_py_sum(const double *v, int n, unsigned npmask) { return py_sum(v, n, npmask); }
+
+/* ------------------------------------------------------------------ split_path (path_plan/path_planner.py:112-192)
+ * Sequential restatement.  compute_cosin = 1 - scipy.spatial.distance.cosine(v1, v2) (:126-133): scipy 1.18
+ * correlation(centered=False) is  dist = 1.0 - uv / math.sqrt(uu * vv)  with uv, uu, vv = np.dot (2-element ddot of the
+ * installed BLAS: fma(a1, b1, a0 * b0), pinned by tests/golden/leaf_split.npz), then np.clip(dist, 0, 2); a zero
+ * displacement gives 0/0 = NaN and NaN < 0 is False.  Segments are written back to back into out (rows x, y, theta),
+ * their lengths into seg_len; info = {status, n segments, change_gear, n points}; status 0 ok, 1 = IndexError at :181
+ * (no gear change), 3 = capacity. */
+void orc_split_path(const orc_map *m, const avp_config *cfg, int nf, const double *p, double *out, int cap_pts,
+                    int32_t *seg_len, int cap_seg, int32_t *info) {
+  int start = 0, change = 0, have = 0, nseg = 0, npts = 0, over = 0;
+  double ext[64][3];
+  int next = cfg->extended_num < 64 ? cfg->extended_num : 64;
+#define SP_PUT(at, x, y, t) do { if ((at) < cap_pts) { out[3 * (at)] = (x); out[3 * (at) + 1] = (y); out[3 * (at) + 2] = (t); } else over = 1; } while (0)
+  for (int i = 0; i < nf - 2; ++i) {
+    double u0 = p[3 * (i + 1)] - p[3 * i], u1 = p[3 * (i + 1) + 1] - p[3 * i + 1];                   /* :127-128 */
+    double v0 = p[3 * (i + 2)] - p[3 * (i + 1)], v1 = p[3 * (i + 2) + 1] - p[3 * (i + 1) + 1];       /* :130-131 */
+    double uv = fma(u1, v1, u0 * v0), uu = fma(u1, u1, u0 * u0), vv = fma(v1, v1, v0 * v0);
+    double dist = 1.0 - uv / sqrt(uu * vv);
+    if (dist < 0.0) dist = 0.0; else if (dist > 2.0) dist = 2.0;
+    double compute_cosin = 1 - dist;
+    if (!(compute_cosin < 0)) continue;                                                              /* :136 */
+    change++;
+    int end = i + 2, len = 0;
+    if (change > 1 && have > 0) {                                                                    /* :141-149 */
+      for (int j = 0; j < have; ++j) SP_PUT(npts + j, ext[have - 1 - j][0], ext[have - 1 - j][1], ext[have - 1 - j][2]);
+      len = have; have = 0;
+    }
+    for (int r = start; r < end; ++r, ++len) SP_PUT(npts + len, p[3 * r], p[3 * r + 1], p[3 * r + 2]);   /* :139 */
+    for (int j = 0; j < next; ++j) {                                                                 /* :152-174 */
+      double xi = p[3 * i], thi = p[3 * i + 2], xn = p[3 * (i + 1)], yn = p[3 * (i + 1) + 1], thn = p[3 * (i + 1) + 2];
+      int f1 = (xn > xi) && (thi > -PI / 2 && thi < PI / 2);
+      int f2 = (xn < xi) && ((thi > PI / 2 && thi < PI) || (thi > -PI && thi < -PI / 2));
+      double speed = (f1 || f2) ? cfg->max_v : -cfg->max_v;
+      double td = speed * cfg->ddt * (j + 1);
+      double xj = xn + td * cos(thn), yj = yn + td * sin(thn);
+      if (!orc_check(m, cfg, xj, yj, thn)) {
+        SP_PUT(npts + len, xj, yj, thn);
+        ext[have][0] = xj; ext[have][1] = yj; ext[have][2] = thn; ++have; ++len;
+      }
+    }
+    if (nseg < cap_seg) seg_len[nseg] = len; else over = 1;
+    ++nseg; npts += len; start = i + 1;                                                              /* :176-177 */
+  }
+  int status = 0;
+  if (nseg == 0) status = 1;                                                                         /* :181 split_path[-1] on [] */
+  else {
+    int len = 0;
+    if (have > 0) { for (int j = 0; j < have; ++j) SP_PUT(npts + j, ext[have - 1 - j][0], ext[have - 1 - j][1], ext[have - 1 - j][2]); len = have; }   /* :183-188 */
+    for (int r = start; r < nf; ++r, ++len) SP_PUT(npts + len, p[3 * r], p[3 * r + 1], p[3 * r + 2]);   /* :180 */
+    if (nseg < cap_seg) seg_len[nseg] = len; else over = 1;
+    ++nseg; npts += len;
+  }
+#undef SP_PUT
+  if (over) status = 3;
+  info[0] = status; info[1] = nseg; info[2] = change; info[3] = npts;
+}

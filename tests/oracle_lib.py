@@ -78,6 +78,7 @@ def lib():
         L.orc_dij_n_ids.restype = ctypes.c_long
         L.orc_dij_n_ids.argtypes = [ctypes.c_void_p]
         L.orc_dij_hvalues.argtypes = [ctypes.c_void_p, c_ip]
+        L.orc_split_path.argtypes = [ctypes.c_void_p, ctypes.POINTER(AvpConfig), ctypes.c_int, c_dp, c_dp, ctypes.c_int, c_ip, ctypes.c_int, c_ip]
         L.orc_plan.restype = ctypes.c_int
         L.orc_plan.argtypes = [ctypes.c_void_p, ctypes.POINTER(AvpConfig), ctypes.POINTER(PlanOut)]
         L.orc_corridor.argtypes = [ctypes.c_void_p, ctypes.POINTER(AvpConfig), ctypes.c_double, ctypes.c_int, c_dp, c_dp, c_ip]
@@ -148,6 +149,18 @@ class OracleMap:
         st = np.zeros(p.shape[0], dtype=np.int32)
         lib().orc_corridor(self._h, ctypes.byref(cfg), float(expand_dis), p.shape[0], _dp(p), _dp(out), _ip(st))
         return out, st
+
+    def split_path(self, cfg, path, cap_pts=None, cap_seg=64):
+        """PathPlanner.split_path(final_path) -> dict(status, segments: list of (len, 3) arrays, change_gear, out_final_path)"""
+        p = np.ascontiguousarray(np.asarray(path, dtype=np.float64).reshape(-1, 3))
+        cap_pts = cap_pts or (len(p) + 64 * (1 + 2 * int(cfg.extended_num)) + 8)
+        out = np.zeros((cap_pts, 3)); seg = np.zeros(cap_seg, dtype=np.int32); info = np.zeros(4, dtype=np.int32)
+        lib().orc_split_path(self._h, ctypes.byref(cfg), len(p), _dp(p), _dp(out), cap_pts, _ip(seg), cap_seg, _ip(info))
+        st, ns, cg, npt = (int(v) for v in info)
+        segs, o = [], 0
+        for k in range(min(ns, cap_seg)):
+            segs.append(out[o:o + int(seg[k])].copy()); o += int(seg[k])
+        return dict(status=st, segments=segs, change_gear=cg, out_final_path=out[:min(npt, cap_pts)].copy(), seg_len=seg[:ns].copy())
 
     def expand_pure(self, cfg, parent):
         n = 2 * cfg.steering_angle_num

@@ -1,5 +1,7 @@
-"""Per-phase cycle counters of the pipelined pass-2 kernel (k_search_pipe) on the bench workload.
-Commit warp (thread 0) and evaluators (thread 32) keep separate accumulators (avp_search_pipe.cuh)."""
+"""Per-phase cycle counters of the search kernel (k_plan) on the bench workload.  Needs the profiling build:
+    tools/build_variant.sh prof -DAVP_PROFILE;  AVP_B200_LIB=$PWD/automatedvaletparking_b200/libavp_b200_prof.so python tools/gpu_pipe_profile.py
+Commit warp (thread 0) and evaluators (thread 32) keep separate accumulators (avp_plan.cuh); the counters of all run segments
+(quanta) of a scenario are summed."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
@@ -63,7 +65,7 @@ if len(long_):
 # the scenarios that set the launch time: total cycles of the commit warp (init + phases 1..4), slowest first
 tot = pr[:, 0:5].sum(1).astype(np.float64)
 order = np.argsort(-tot)[:10]
-print('slowest scenarios (pass 2): scen pops Gcycles | per pop: lookups commit heappop help+wait | dijkstra/pop resumes pushes/pop init(Mcycles)')
+print('slowest scenarios: scen pops Gcycles | per pop: lookups commit heappop help+wait | dijkstra/pop resumes pushes/pop init(Mcycles)')
 for i in order:
     if s['n_pops'][i] < 1024:
         continue
@@ -88,3 +90,8 @@ if len(long_):
         np.mean(alone) if alone else 0, max(alone) if alone else 0, len(alone), np.mean(part) if part else 0, max(part) if part else 0, len(part),
         np.mean(full) if full else 0, max(full) if full else 0, len(full)))
     print('  (Gcycles, smid, pops on the sibling SM): ' + ' '.join('%.2f/%d/%d' % r for r in rows))
+
+if len(long_):
+    sub = wp[long_][:, 8:10, 16:24].reshape(len(long_), 16).astype(np.float64) / s['n_pops'][long_].astype(np.float64)[:, None]
+    print('serial section A->B of the commit warp, cycles/pop (long scenarios): ' +
+          ' '.join('%s %.0f' % (nm, v) for nm, v in zip(['A..start', 'ctl', 'accept', 'lookup loads', 'skip+g+h', 'predict', 'target', 'queue init', 'tick'], sub.mean(0)[:9])))
