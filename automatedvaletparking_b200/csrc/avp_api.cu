@@ -26,7 +26,7 @@ struct avp_ctx {
   int32_t *d_nv = nullptr, *d_vert_off = nullptr; double *d_verts = nullptr;
   uint8_t *d_cost = nullptr; int64_t cost_bytes = 0;
   int32_t *d_col = nullptr; int64_t col_count = 0;
-  double2 *d_cells = nullptr; int64_t cell_count = 0;
+  double2 *d_cells = nullptr; int64_t cell_count = 0; long long *d_cell_total = nullptr;
   bool rasterised = false;
   // byte capacities of the scenario arrays: uploads of a same-sized batch reuse the allocations (cudaMalloc/cudaFree are
   // synchronising and cost far more than the H2D copies of a batch)
@@ -93,12 +93,13 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return -8; }
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
-  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512));
-  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256));
+  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512) + AVP_CELL_SMEM);
+  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256) + AVP_CELL_SMEM);
+  cudaFuncSetAttribute(k_plan<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(640) + AVP_CELL_SMEM);
   {
     int o = 0;
-    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, 12 * avp_sm_open(512)) == cudaSuccess && o > 0) ? o : 1;
-    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, 12 * avp_sm_open(256)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, 12 * avp_sm_open(512) + AVP_CELL_SMEM) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, 12 * avp_sm_open(256) + AVP_CELL_SMEM) == cudaSuccess && o > 0) ? o : 1;
   }
   ctx->slots = ctx->n_sm * ctx->ctas_per_sm[0];               // persistent grids: multiples of the SM count
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evM);
@@ -131,7 +132,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
-  free_dev(ctx->d_counter); free_dev(ctx->d_scratch);
+  free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_cell_total);
   free_dev(ctx->d_order);
   free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1); if (ctx->evM) cudaEventDestroy(ctx->evM);
@@ -166,6 +167,7 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
     S.nx = (int)((S.b[1] - S.b[0]) / ds); S.ny = (int)((S.b[3] - S.b[2]) / ds);           // costmap.py:182-185
     if (S.nx < 3 || S.ny < 3 || S.nx > 16384 || S.ny > 16384) FAIL("avp_scenarios_upload: map extent out of range");
     S.stepx = (S.b[1] - S.b[0]) / (S.nx - 1); S.stepy = (S.b[3] - S.b[2]) / (S.ny - 1);   // np.linspace step
+    S.inv_stepx = 1.0 / S.stepx;
     volatile double x1 = 1.0 * S.stepx, y1 = 1.0 * S.stepy; x1 = x1 + S.b[0]; y1 = y1 + S.b[2];
     S.dx = x1 - S.b[0]; S.dy = y1 - S.b[2];                                                  // costmap.py:190-191
     S.stride = (int)((S.b[1] - S.b[0]) / S.dx); S.mx = S.stride; S.my = (int)((S.b[3] - S.b[2]) / S.dy);
@@ -173,7 +175,7 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
     S.n_ids = (int32_t)(H * S.stride + W + 8);
     S.obs_begin = obs_off[i]; S.obs_end = obs_off[i + 1];
     S.cost_off = cost_off; cost_off += (int64_t)S.nx * S.ny; cost_off = (cost_off + 15) & ~15ll;
-    S.col_off = col_off; col_off += S.nx + 1;
+    S.col_off = col_off; col_off += (S.nx + 1 + 3) & ~3;        // 16-byte aligned: the column starts are bulk-copied to shared memory (k_plan)
     S.id_off = id_off; id_off += (S.n_ids + 3) & ~3;
   }
   {   // longest-first order for the persistent CTAs' work counter (the eager Dijkstra grows with the start-goal distance)
@@ -218,20 +220,27 @@ extern "C" int avp_rasterise(avp_ctx *ctx) {
   if (ctx->n <= 0) FAIL("avp_rasterise: no scenarios uploaded");
   CK(cudaSetDevice(ctx->device));
   const int n = ctx->n;
+  if (!ctx->d_cell_total) CK(cudaMalloc(&ctx->d_cell_total, 2 * sizeof(long long)));
+  if (!ctx->d_cells) CK(ensure_dev(&ctx->d_cells, &ctx->cap_cells, sizeof(double2) * 1024));
   CK(cudaMemsetAsync(ctx->d_cost, 0, (size_t)ctx->cost_bytes, ctx->stream));
   k_raster<<<n, 64, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_nv, ctx->d_vert_off, ctx->d_verts, ctx->d_cost); ctx->launches++;
   k_count_cols<<<n, 128, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_cost, ctx->d_col); ctx->launches++;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ctx->h_scen.data(), ctx->d_scen, sizeof(ScenDev) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  int64_t cell_off = 0;
-  for (int i = 0; i < n; ++i) { ScenDev &S = ctx->h_scen[i]; S.cell_off = cell_off; S.cell_cap = S.n_obs; cell_off += (S.n_obs + 1) & ~1; }
-  ctx->cell_count = cell_off;
-  CK(ensure_dev(&ctx->d_cells, &ctx->cap_cells, sizeof(double2) * (cell_off + 1)));
-  CK(cudaMemcpyAsync(ctx->d_scen, ctx->h_scen.data(), sizeof(ScenDev) * n, cudaMemcpyHostToDevice, ctx->stream));
-  k_fill_cells<<<n, 128, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_cost, ctx->d_col, ctx->d_cells); ctx->launches++;
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(ctx->stream));
+  // cell offsets by a device-side scan; the fill runs against the current capacity of the (grow-only) cell list and only a batch
+  // that needs more than any batch before it costs a second round
+  long long tot[2] = {0, 0};
+  for (int round = 0; round < 2; ++round) {
+    k_scan_cells<<<1, 1024, 0, ctx->stream>>>(n, ctx->d_scen, (long long)(ctx->cap_cells / sizeof(double2)) - 1, ctx->d_cell_total); ctx->launches++;
+    k_fill_cells<<<n, 128, 0, ctx->stream>>>(n, ctx->d_scen, ctx->d_cost, ctx->d_col, ctx->d_cells, ctx->d_cell_total); ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tot, ctx->d_cell_total, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_scen.data(), ctx->d_scen, sizeof(ScenDev) * n, cudaMemcpyDeviceToHost, ctx->stream));      // n_obs, raster_error, offsets for the host-side queries
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!tot[1]) break;
+    if (round == 1) FAIL("avp_rasterise: the obstacle cell list could not be sized");
+    free_dev(ctx->d_cells); ctx->d_cells = nullptr; ctx->cap_cells = 0;
+    CK(ensure_dev(&ctx->d_cells, &ctx->cap_cells, sizeof(double2) * (size_t)(tot[0] + tot[0] / 8 + 1024)));
+  }
+  ctx->cell_count = tot[0];
   ctx->rasterised = true;
   return 0;
 }
@@ -359,7 +368,7 @@ extern "C" int avp_rs_optimal(avp_ctx *ctx, int m, const double *q, double maxc,
 static int ensure_ws(avp_ctx *ctx, int ctas) {
   const int nchild = 2 * ctx->cfg.steering_angle_num;
   const int max_pops = ctx->cfg.max_pops > 0 ? ctx->cfg.max_pops : 20000;
-  const int node_cap = nchild * (max_pops + 1) + 2;
+  const int node_cap = (nchild * (max_pops + 1) + 2 + 7) & ~7;       // multiple of 8: every slot's 16-byte heap records start on a 128-byte line
   const int n = ctx->n;
   if (ctx->ws_n >= n && ctx->ws_n <= 4 * n + 64 && ctx->ws_ctas >= ctas && ctx->node_cap == node_cap) return 0;      // grow-only with slack
   free_ws(ctx);
@@ -444,8 +453,8 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   // CTA width: 512 threads, one CTA per SM (15 evaluator warps per pop: the shortest pop), or 256 threads, two CTAs per SM
   // (more searches in flight per SM: throughput for batches with far more long searches than SMs)
   int block = 512;
-  { const char *be = getenv("AVP_PLAN_BLOCK"); if (be && atoi(be) == 256) block = 256; }
-  const int per_sm = ctx->ctas_per_sm[block == 512 ? 0 : 1];
+  { const char *be = getenv("AVP_PLAN_BLOCK"); if (be && (atoi(be) == 256 || atoi(be) == 640)) block = atoi(be); }
+  const int per_sm = block == 256 ? ctx->ctas_per_sm[1] : 1;
   int grid = ctx->n_sm * per_sm; if (grid > ctx->n) grid = ctx->n;
   if (ensure_ws(ctx, ctx->n_sm * ctx->ctas_per_sm[1] > grid ? ctx->n_sm * ctx->ctas_per_sm[1] : grid)) return -1;
   PlanParams PP; memset(&PP, 0, sizeof(PP));
@@ -465,7 +474,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   // SM pairs: only when the grid covers every SM (else the hardware's placement decides) and not switched off (AVP_SPREAD=0)
   { const char *se = getenv("AVP_SPREAD"); P.spread = (grid == ctx->n_sm * per_sm && ctx->n_sm >= 4 && !(se && atoi(se) == 0)) ? 1 : 0; }
   { const char *me = getenv("AVP_SPREAD_MAX"); PP.spread_max = me ? atoi(me) : (ctx->n_sm / 2 + ctx->n_sm / 4) * per_sm; }
-#ifdef AVP_PROFILE
+#if defined(AVP_PROFILE) || defined(AVP_PROFILE_LIGHT)
   CK(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * (size_t)ctx->n * 16, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_wprof, 0, sizeof(long long) * (size_t)ctx->n * 384, ctx->stream));
 #endif
@@ -477,8 +486,9 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
     k_dij_eager<<<dgrid, AVP_DIJ_WARPS * 32, 0, ctx->stream>>>(PP); ctx->launches++;
   }
   CK(cudaEventRecord(ctx->evM, ctx->stream));
-  if (block == 512) k_plan<512><<<grid, 512, 12 * avp_sm_open(512), ctx->stream>>>(PP);
-  else k_plan<256><<<grid, 256, 12 * avp_sm_open(256), ctx->stream>>>(PP);
+  if (block == 512) k_plan<512><<<grid, 512, 12 * avp_sm_open(512) + AVP_CELL_SMEM, ctx->stream>>>(PP);
+  else if (block == 640) k_plan<640><<<grid, 640, 12 * avp_sm_open(640) + AVP_CELL_SMEM, ctx->stream>>>(PP);
+  else k_plan<256><<<grid, 256, 12 * avp_sm_open(256) + AVP_CELL_SMEM, ctx->stream>>>(PP);
   ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());

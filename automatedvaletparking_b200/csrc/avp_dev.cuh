@@ -22,6 +22,7 @@ struct ScenDev {
   double b[4];           // boundary (costmap.py:169-172)
   double dx, dy;         // _discrete_x/_y (costmap.py:190-191)
   double stepx, stepy;   // np.linspace step (b1-b0)/(nx-1)
+  double inv_stepx;      // 1 / stepx: first guess of a column index (col_range), never decides anything
   int32_t nx, ny;        // cost_map.shape
   int32_t stride;        // int((b1-b0)/dx): row stride of convert_position_to_index (costmap.py:327-328)
   int32_t mx, my;        // is_obstacle clamp (compute_h.py:243-246)
@@ -243,7 +244,7 @@ __device__ __forceinline__ bool cell_hits(const VehGeom &g, double ox, double oy
 // the np.where order, which is sorted by column).
 __device__ __forceinline__ void col_range(const ScenDev &S, double x_min, double x_max, int &lo, int &hi) {
   const int nx = S.nx;
-  const double inv = 1.0 / S.stepx;                 // initial guesses only: the loops below settle the exact bounds
+  const double inv = S.inv_stepx;                   // initial guesses only: the loops below settle the exact bounds
   int a = (int)floor((x_min - S.b[0]) * inv) - 1; if (a < 0) a = 0; if (a > nx - 1) a = nx - 1;
   while (a > 0 && lin_at(S.b[0], S.b[1], S.stepx, nx, a - 1) >= x_min) --a;
   while (a < nx && !(lin_at(S.b[0], S.b[1], S.stepx, nx, a) >= x_min)) ++a;

@@ -166,7 +166,23 @@ __global__ void k_count_cols(int n_scen, ScenDev *scen, const uint8_t *cost, int
   }
 }
 
-__global__ void k_fill_cells(int n_scen, const ScenDev *scen, const uint8_t *cost, const int32_t *col_start, double2 *cells) {
+// cell_off / cell_cap of every scenario = exclusive prefix sum of the (even-padded) obstacle counts, on the device (one CTA);
+// total[0] = entries needed, total[1] = 1 if that exceeds the capacity of the cell list (the host then grows it and repeats)
+__global__ void __launch_bounds__(1024) k_scan_cells(int n_scen, ScenDev *scen, long long cap, long long *total) {
+  __shared__ long long s_part[1024];
+  const int t = threadIdx.x, per = (n_scen + 1023) / 1024, beg = t * per, end = min(beg + per, n_scen);
+  long long acc = 0;
+  for (int i = beg; i < end; ++i) acc += (scen[i].n_obs + 1) & ~1;
+  s_part[t] = acc;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) { const long long v = (t >= o) ? s_part[t - o] : 0; __syncthreads(); s_part[t] += v; __syncthreads(); }
+  long long off = s_part[t] - acc;
+  for (int i = beg; i < end; ++i) { scen[i].cell_off = off; scen[i].cell_cap = scen[i].n_obs; off += (scen[i].n_obs + 1) & ~1; }
+  if (t == 1023) { total[0] = s_part[1023]; total[1] = (s_part[1023] > cap) ? 1 : 0; }
+}
+
+__global__ void k_fill_cells(int n_scen, const ScenDev *scen, const uint8_t *cost, const int32_t *col_start, double2 *cells, const long long *total) {
+  if (total[1]) return;            // the cell list is too small: nothing is written, the host grows it and launches again
   const int s = blockIdx.x;
   if (s >= n_scen) return;
   const ScenDev &S = scen[s];
@@ -446,6 +462,12 @@ __global__ void __launch_bounds__(128) k_rs_optimal(int m, const double *q, doub
 // on it the first AVP_SM_HEAP entries live in shared memory (sheap) and gheap[0 .. AVP_SM_HEAP) is their save area
 // (dij_heap_load / dij_heap_store), so a search can be suspended on one SM and resumed on another.
 
+#ifdef AVP_NO_PREFETCH      // A/B build
+__device__ __forceinline__ void prefetch_l1(const void *) { }
+#else
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
+
 struct DijCtx {
   const ScenDev *S; const uint8_t *cost;
   int32_t *hval, *ost; double *gx, *gy;
@@ -571,6 +593,14 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
     top = shfl_u64(top, 0);
     const int cur_id = (int)(unsigned)top;
     const double nxt_x = gxa[cur_id], nxt_y = gya[cur_id];     // issued before the sift so that the latency overlaps it
+    // the popped cell is expanded next: its neighbours' state words and cost-map bytes are prefetched while lane 0 sifts (the
+    // positions are estimated from the id -- ids and raster indices are floors of the same lattice coordinates; a wrong guess
+    // only costs the prefetch)
+    if (lane >= 1 && lane <= 6) {
+      const int i1 = cur_id / stride, i0 = cur_id - i1 * stride;
+      if (lane <= 3) { const int q = (i1 + lane - 2) * stride + i0 - 1; if (q >= 0 && q + 2 < n_ids) { prefetch_l1(&ost[q]); prefetch_l1(&ost[q + 2]); } }
+      else { const int xi = i0 - 1 + (lane - 5), yi = my - i1 - 3; if (xi >= 0 && xi < nx && yi >= 0 && yi + 2 < ny) { prefetch_l1(&cost[(size_t)xi * ny + yi]); prefetch_l1(&cost[(size_t)xi * ny + yi + 2]); } }
+    }
     if (lane == 0) {
       const unsigned long long item = HP_GET(hn - 1);
       const int n = hn - 1;
@@ -698,6 +728,33 @@ __device__ __forceinline__ void oh_get(const double *sf, const int32_t *si, cons
   else { const int4 v = *reinterpret_cast<const int4 *>(&ge[i]); f = __hiloint2double(v.y, v.x); idx = v.z; }
 }
 #define OH_SET(i, f_, idx_) do { if ((i) < SMO) { sf[(i)] = (f_); si[(i)] = (idx_); } else { int4 v_; v_.x = __double2loint(f_); v_.y = __double2hiint(f_); v_.z = (idx_); v_.w = 0; *reinterpret_cast<int4 *>(&ge[(i)]) = v_; } nodes[(idx_)].hpos = (i); } while (0)
+// The sifts are chains of dependent loads: below the shared-memory head every level is a DRAM / L2 round trip (the heaps of the
+// long searches do not fit the L2 together).  The addresses of the next levels are known before their data is needed, so they
+// are prefetched (no effect on any result):
+//   push  the ancestors of the next k positions [n, n + k) are contiguous per level: one or two lines per level, all of them at once
+//   pop   the four levels below a position are four contiguous ranges (32, 64, 128, 256 bytes): one round trip per four levels
+template <int SMO>
+__device__ __forceinline__ void oh_prefetch_push(const OEnt *ge, int n, int k, int lane) {
+  // lane l: the level-l ancestors ((p + 1) >> l) - 1 of p in [n, n + k): at most k / 2^l + 1 adjacent entries
+  if (lane >= 1 && lane < 24) {
+    const int lo = ((n + 1) >> lane) - 1, hi = ((n + k) >> lane) - 1;
+    if (hi >= SMO && lo >= 0) { prefetch_l1(&ge[lo < SMO ? SMO : lo]); prefetch_l1(&ge[hi]); }
+  }
+}
+template <int SMO>
+__device__ __forceinline__ void oh_prefetch_subtree(const OEnt *ge, int pos, int last) {
+  int lo = 2 * pos + 1, cnt = 2;               // level d below pos: entries [lo, lo + cnt), 16 bytes each
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    if (lo >= last) break;
+    int hi = lo + cnt - 1; if (hi >= last) hi = last - 1;
+    if (hi >= SMO) {
+      prefetch_l1(&ge[lo < SMO ? SMO : lo]); prefetch_l1(&ge[hi]);
+      if (cnt == 16 && lo + 8 <= hi && lo + 8 >= SMO) prefetch_l1(&ge[lo + 8]);
+    }
+    lo = 2 * lo + 1; cnt *= 2;
+  }
+}
 template <int SMO>
 __device__ __forceinline__ void oh_siftdown(double *sf, int32_t *si, OEnt *ge, Node *nodes, int pos, double fi, int item) {   // heapq._siftdown(heap, 0, pos)
   while (pos > 0) {
@@ -719,9 +776,10 @@ __device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, OEnt *ge, No
   double fi; int item; oh_get<SMO>(sf, si, ge, last, fi, item);
   n = last;
   if (last == 0) return;
-  int pos = 0, child = 1;
+  int pos = 0, child = 1, lvl = 0;
   while (child < last) {
     const int right = child + 1;
+    if (2 * child + 2 >= SMO && (lvl++ & 3) == 0) oh_prefetch_subtree<SMO>(ge, pos, last);      // the next four levels in one round trip
     double cf; int ci; oh_get<SMO>(sf, si, ge, child, cf, ci);
     if (right < last) { double rf; int ri; oh_get<SMO>(sf, si, ge, right, rf, ri); if (!(cf < rf)) { child = right; cf = rf; ci = ri; } }
     OH_SET(pos, cf, ci); pos = child; child = 2 * pos + 1;

@@ -45,10 +45,23 @@ enum { CTL_FINISH = 2 };
 // that a warp runs one word formula where possible (4 instances per family: 3 + 1 left over).  Ordered by measured cost,
 // longest first (profiles/: 21 k ... 3 k cycles per item); a left-over item with three different formulas costs the sum of
 // the three (41 k cycles for {9,29,37}), so those instances are items of their own.
+#ifndef AVP_RS_FINE
 #define RS_NITEM 19
 __device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
   {45, 13, 17}, {0, 1, -1}, {6, 7, 8}, {5, 33, 41}, {20, 21, -1}, {22, 23, -1}, {10, 11, 12}, {14, 15, 16}, {26, 27, 28},
   {34, 35, 36}, {24, 25, -1}, {9, -1, -1}, {29, -1, -1}, {37, -1, -1}, {2, 3, 4}, {38, 39, 40}, {30, 31, 32}, {42, 43, 44}, {18, 19, -1}};
+#else
+// A/B variant: one word instance x all successors per warp item (10 of 32 lanes, no divergence between instances: the item is as
+// long as ONE formula), the sub-step chains (the longest items) first, one selection per successor: a shorter critical path
+// through the evaluation for the same work
+#define RS_NITEM 46
+__device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
+  {45, -1, -1}, {13, -1, -1}, {17, -1, -1}, {0, -1, -1}, {1, -1, -1}, {6, -1, -1}, {7, -1, -1}, {8, -1, -1}, {5, -1, -1}, {33, -1, -1}, {41, -1, -1},
+  {20, -1, -1}, {21, -1, -1}, {22, -1, -1}, {23, -1, -1}, {10, -1, -1}, {11, -1, -1}, {12, -1, -1}, {14, -1, -1}, {15, -1, -1}, {16, -1, -1},
+  {26, -1, -1}, {27, -1, -1}, {28, -1, -1}, {34, -1, -1}, {35, -1, -1}, {36, -1, -1}, {24, -1, -1}, {25, -1, -1}, {9, -1, -1}, {29, -1, -1}, {37, -1, -1},
+  {2, -1, -1}, {3, -1, -1}, {4, -1, -1}, {38, -1, -1}, {39, -1, -1}, {40, -1, -1}, {30, -1, -1}, {31, -1, -1}, {32, -1, -1}, {42, -1, -1}, {43, -1, -1}, {44, -1, -1},
+  {18, -1, -1}, {19, -1, -1}};
+#endif
 
 struct PureRes {
   double cpose[AVP_NCHILD_MAX][3];

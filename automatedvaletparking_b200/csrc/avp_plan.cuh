@@ -64,6 +64,29 @@ __device__ __forceinline__ void ring_push(int *tail, int32_t *buf, int mask, int
   while (atomicCAS(&buf[t & mask], -1, v) != -1) { if (++spins > (1ll << 28)) return; }
 }
 
+// ---- TMA (bulk asynchronous copy, cp.async.bulk + mbarrier) of a scenario's obstacle cell list and column starts into shared
+// memory when a CTA takes the scenario over: every collision check of the following quantum (about 40 per pop) scans that
+// list (collision_check.py:55-69), so it is staged once instead of being re-fetched through L1 beside the node / heap /
+// table traffic.  Lists larger than AVP_CELL_SMEM stay in global memory (same code path, generic loads).
+#ifndef AVP_CELL_SMEM
+#define AVP_CELL_SMEM (48 * 1024)
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tAVP_MBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra AVP_MBAR_WAIT;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __global__ void k_plan_init(PlanParams P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= P.q_mask) P.queue[i] = (i < P.K.n_work) ? (P.K.work_list ? P.K.work_list[i] : i) : -1;
@@ -119,9 +142,17 @@ __global__ void __launch_bounds__(AVP_DIJ_WARPS * 32) k_dij_eager(PlanParams P) 
 #else
 #define PROF(...)
 #endif
+// AVP_PROFILE_LIGHT: four shared-memory accumulators and nothing else (the full profile's counters live in local memory and
+// perturb the commit warp): [0] evaluators waiting at barrier A, [1] barrier A -> barrier B as the evaluators see it (the
+// serial section), [2] commit warp waiting at barrier A, [3] pops; written to prof[sc][0..3]
+#ifdef AVP_PROFILE_LIGHT
+#define LPROF(...) __VA_ARGS__
+#else
+#define LPROF(...)
+#endif
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
+__global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_plan(PlanParams PP) {
   static_assert(BLOCK >= 128 && BLOCK % 32 == 0, "one commit warp + at least three evaluator warps");
   const KParams &P = PP.K;
   constexpr int SMO = avp_sm_open(BLOCK);
@@ -148,6 +179,10 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
   __shared__ int s_work2, s_work3, s_rs_done, s_course_rdy, s_q_rdy, s_sub_rdy, s_ins_done, s_cstride;   // the evaluators' queue: tail counter, finished rs items, course / rs queries / sub-step poses published, table inserts of the running commit done, stride of the course point order
   __shared__ VehGeom s_vg[BLOCK / 32];           // per warp: the vehicle rectangle of the pose being checked (check_distance_warp_sm)
   __shared__ DijCtx s_D;
+  __shared__ __align__(8) unsigned long long s_cell_bar;       // mbarrier of the staged cell list
+  unsigned char *s_cells = s_dyn + 12 * SMO;                   // AVP_CELL_SMEM bytes: double2 cells, then the int32 column starts
+  unsigned cell_parity = 0;
+  LPROF(__shared__ long long s_lp[4]; __shared__ long long s_lpe, s_lpc;)
 #ifdef AVP_PROFILE
   __shared__ int s_trace_on;
   __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts)
@@ -165,6 +200,8 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
   PlanCtl *ctl = PP.ctl;
 
   if (tid == 0) { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); s_odd = (int)(sm_ & 1u); }
+  if (tid == 0) mbar_init(&s_cell_bar, 1);
+  __syncthreads();
 
   for (;;) {
     // ---- take the head of the run queue (thread 0).  The CTAs on odd SM ids stand back while few scenarios are live (see the
@@ -210,6 +247,17 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
     const ScenDev &S = P.scen[sc];
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
+    const unsigned cell_bytes = (unsigned)S.n_obs * (unsigned)sizeof(double2), col_bytes = (((unsigned)S.nx + 1u) * 4u + 15u) & ~15u;
+    const bool staged = slot >= 0 && S.n_obs > 0 && cell_bytes + col_bytes <= AVP_CELL_SMEM;
+    if (staged) {
+      if (tid == 0) {
+        mbar_expect_tx(&s_cell_bar, cell_bytes + col_bytes);
+        bulk_g2s(s_cells, cells, cell_bytes, &s_cell_bar);
+        bulk_g2s(s_cells + cell_bytes, col_start, col_bytes, &s_cell_bar);
+      }
+      cells = reinterpret_cast<const double2 *>(s_cells);
+      col_start = reinterpret_cast<const int32_t *>(s_cells + cell_bytes);
+    }
     int32_t *hval = P.hval + S.id_off, *ost = P.ost + S.id_off;
     unsigned long long *dgheap = P.dheap + (size_t)sc * P.dheap_cap;
     const double goal[3] = {S.pose[3], S.pose[4], pi_2_pi(S.pose[5])};
@@ -302,13 +350,16 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
       }
     }
     __syncthreads();
+    if (staged) { mbar_wait(&s_cell_bar, cell_parity); cell_parity ^= 1u; }       // the cell list has landed
     if (tid == 0) do_pop();                      // a fresh search: the first get() returns the root
     PIPE_TICK(0, 0);
     PROF(if (tid == 32) tp = clock_ordered();)
 
     bool reached = false;
+    LPROF(if (tid < 4) s_lp[tid] = 0; if (tid == 32) s_lpe = clock_ordered(); if (tid == 0) s_lpc = clock_ordered();)
     for (;;) {
       __syncthreads();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
+      LPROF(if (tid == 32) { const long long t_ = clock_ordered(); s_lp[0] += t_ - s_lpe; s_lpe = t_; } if (tid == 0) { s_lp[2] += clock_ordered() - s_lpc; s_lp[3] += 1; })
       PIPE_TICK(0, 4);                           // commit warp waiting for the evaluators
       PROF(if (tid == 0) st_ = clock_ordered();)
       TS(0);
@@ -434,6 +485,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
       SUBT(8);
       TS(1);
       __syncthreads();                                 // ---- barrier B: target published
+      LPROF(if (tid == 32) { s_lp[1] += clock_ordered() - s_lpe; })
       TS(2);
       PIPE_TICK(32, 15);                         // evaluators waiting for the target
       if (s_ctlB != CTL_RUN) { reached = (s_ctlB == CTL_FINISH); break; }
@@ -473,6 +525,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
           // whose h value is already in the table; a miss resumes the Dijkstra search, which is warp-collective.
           int i = 0, n_miss = 0;
           int on = s_on;
+          oh_prefetch_push<SMO>(oge, on, nchild, lane);            // the ancestors of the positions this commit pushes to
           for (;;) {
             int stop = nchild;
             if (lane == 0) {
@@ -540,12 +593,12 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
         // ---- the commit warp joins the evaluators' queue (initialised before barrier B)
         __syncwarp();
         T = s_tgt;
-        if (!T.valid) continue;
+        if (!T.valid) { LPROF(if (tid == 0) s_lpc = clock_ordered();) continue; }
         WP_START();
       } else {
         // =========================== EVALUATORS ===========================
         T = s_tgt;
-        if (!T.valid) continue;
+        if (!T.valid) { LPROF(if (tid == 32) s_lpe = clock_ordered();) continue; }
         WP_START();
         TS(3); TS(4);
       }
@@ -693,10 +746,16 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
             }
 #endif
             if (lane < nchild) { W.found[lane] = fnd; W.hv[lane] = hv; }
+#ifdef AVP_RS_FINE
+          } else if (it >= 4 + nchild) {
+            const int rs_it = it - 4 - nchild;
+#else
           } else if (it <= 3 + RS_NITEM) {
+            const int rs_it = it - 4;
+#endif
             if (!wait_ge_cta(&s_q_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
             const int k = lane / nchild, row = lane - k * nchild;
-            const int inst = (k < 3) ? rs_item_inst[it - 4][k] : -1;
+            const int inst = (k < 3) ? rs_item_inst[rs_it][k] : -1;
             if (inst >= 0) {
               double t, u, v;
               if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
@@ -709,7 +768,11 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
             if (lane == 0) { __threadfence_block(); add_release_cta(&s_rs_done, 1); }
           } else {
             if (!wait_ge_cta(&s_sub_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+#ifdef AVP_RS_FINE
+            const int i = it - 4;
+#else
             const int i = it - 4 - RS_NITEM;
+#endif
             int coll = 0;
             for (int k = 0; k < nsubs; ++k) {
               bool hit;
@@ -738,10 +801,14 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
         //   rs item is finished (s_rs_done).  A warp takes a selection whenever the rs items are finished, else a course point.
         // the commit warp only helps while E1 items are left: it arrives late, and a selection or a course point taken then
         // would make it the last warp at barrier A
-        if (warp == 0) { WP_ACC(3); continue; }
+        if (warp == 0) { WP_ACC(3); LPROF(if (tid == 0) s_lpc = clock_ordered();) continue; }
         if (!wait_ge_cta(&s_course_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; continue; }
         const int npts = s_npts, cstride = s_cstride;
+#ifdef AVP_RS_FINE
+        const int n_sel = nchild;
+#else
         const int n_sel = (nchild + 1) / 2;
+#endif
         bool sel_left = true, chk_left = npts > 0;
         for (;;) {
           PROF(const long long ti_ = clock64();)
@@ -772,7 +839,11 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
             const double gth = pi_2_pi(gyaw);
             if (check_pose_cs_warp_sm(cfg, S, cells, col_start, gx_, gy_, d_cos(gth), d_sin(gth), vg)) { if (lane == 0) s_shot_coll = 1; }
           } else {
+#ifdef AVP_RS_FINE
+            const int gl = lane, i = (lane < 16) ? it : nchild;
+#else
             const int half = lane >> 4, gl = lane & 15, i = 2 * it + half;
+#endif
             if (i < nchild && gl < RS_NGROUP) rs_select_group(s_cand[i], s_valid[i], gl, 1, 1, maxc, s_grp[i][gl]);
             __syncwarp();
             if (i < nchild && gl == 0) {
@@ -790,9 +861,11 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) k_plan(PlanParams PP) {
 #endif
         }
         WP_ACC(2); TS(7); PIPE_TICK(32, 13);
+        LPROF(if (tid == 32) s_lpe = clock_ordered();)
       }
     }
     __syncthreads();
+    LPROF(if (tid < 4 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
 #ifdef AVP_PROFILE
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] += s_wp[warp][k]; }
     if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_ic[tid];

@@ -1,0 +1,29 @@
+"""Where do the two sides of the pipelined pop wait?  Needs the light profiling build:
+    tools/build_variant.sh lp -DAVP_PROFILE_LIGHT;  AVP_B200_LIB=$PWD/automatedvaletparking_b200/libavp_b200_lp.so python tools/gpu_light_profile.py [workload]
+Four shared-memory accumulators per scenario (avp_plan.cuh), cycles per pop."""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import bench
+from automatedvaletparking_b200.batch import DevicePlanner
+os.environ.setdefault("AVP_HOST_TIMEOUT_S", "300")
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+dp = DevicePlanner(max_pops=20000)
+scs, n_total, scaling, gids = bench.make_workload(name, 0, 1, dp)
+dp.load(scs)
+ms = dp.plan_resident(256, 0); ms = dp.plan_resident(256, 0)
+res = dp.fetch(256, 0)
+pr = dp.phase_profile().astype(np.float64)
+s = res.summaries
+print("search ms %.1f" % ms, dp.last_search_passes(), "successors", res.successors)
+for nm, idx in (("long (20000 pops)", np.where(s["n_pops"] >= 20000)[0]), ("mid (1024..20000)", np.where((s["n_pops"] >= 1024) & (s["n_pops"] < 20000))[0]),
+                ("short (< 1024)", np.where(s["n_pops"] < 1024)[0])):
+    if len(idx) == 0:
+        continue
+    pops = np.maximum(pr[idx, 3], 1.0)
+    print("%-18s n %4d pops/scenario %8.1f | per pop: evaluators wait at A %7.0f | serial section A->B %7.0f | commit warp waits at A %7.0f" %
+          (nm, len(idx), s["n_pops"][idx].mean(), (pr[idx, 0] / pops).mean(), (pr[idx, 1] / pops).mean(), (pr[idx, 2] / pops).mean()))
+dp.close()
