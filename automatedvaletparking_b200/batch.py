@@ -74,6 +74,7 @@ class DevicePlanner:
             raise AvpError(f"avp_create failed (rc={rc}): no usable CUDA device {device}? this package has no CPU path")
         self._h = h
         self.device = int(device)
+        self.plan_epoch = 0            # bumped by every whole search and every upload: they overwrite the per-cell arrays of the single-step Dijkstra
         self.n = 0
         self.batch = None
         self.h2d_bytes = 0
@@ -105,6 +106,7 @@ class DevicePlanner:
     def load(self, scenarios, rasterise: bool = True):
         b = scenarios if isinstance(scenarios, scn.ScenarioBatch) else scn.pack(scenarios)
         self.batch = b
+        self.plan_epoch += 1
         self._ck(self._L.avp_scenarios_upload(self._h, len(b), _dp(b.poses), _ip(b.obs_off), _ip(b.nv), _ip(b.vert_off),
                                               _dp(b.verts), _dp(b.boundary) if b.boundary is not None else None),
                  "avp_scenarios_upload")
@@ -185,6 +187,7 @@ class DevicePlanner:
         sums = np.zeros(n, dtype=SUMMARY_DTYPE)
         paths = np.zeros((n, cap_path, 3))
         pops = np.zeros((n, cap_pops), dtype=np.int32) if cap_pops > 0 else None
+        self.plan_epoch += 1
         self._ck(self._L.avp_plan_batch(self._h, sums.ctypes.data_as(ctypes.c_void_p), _dp(paths), cap_path,
                                         _ip(pops) if pops is not None else None, cap_pops), "avp_plan_batch")
         self.d2h_bytes += sums.nbytes + paths.nbytes + (pops.nbytes if pops is not None else 0)
@@ -194,6 +197,7 @@ class DevicePlanner:
         """Run the search with results left on the device; returns the CUDA-event time in ms."""
         self._ck(self._L.avp_plan_configure(self._h, cap_path, cap_pops), "avp_plan_configure")
         ms = ctypes.c_float()
+        self.plan_epoch += 1
         self._ck(self._L.avp_plan_batch_resident(self._h, ctypes.byref(ms)), "avp_plan_batch_resident")
         return float(ms.value)
 
@@ -229,6 +233,15 @@ class DevicePlanner:
         for k in range(min(ns, cap_seg)):
             segs.append(pts[o:o + int(seg[k])].copy()); o += int(seg[k])
         return st, segs, cg
+
+    def trace_fgh(self, on: bool = True):
+        """record f, g, h of every popped node in the following plans (parity aid; needs cap_pops > 0)"""
+        self._ck(self._L.avp_trace_fgh(self._h, 1 if on else 0), "avp_trace_fgh")
+
+    def pop_fgh(self, cap_pops: int) -> np.ndarray:
+        out = np.zeros((self.n, cap_pops, 3))
+        self._ck(self._L.avp_fetch_pop_fgh(self._h, _dp(out), cap_pops), "avp_fetch_pop_fgh")
+        return out
 
     def result_device_pointers(self):
         s, p = ctypes.c_void_p(), ctypes.c_void_p()

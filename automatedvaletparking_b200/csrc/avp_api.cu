@@ -45,6 +45,7 @@ struct avp_ctx {
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
+  double *d_pop_fgh = nullptr; size_t cap_fgh = 0; bool trace_fgh = false;
   long long *d_prof = nullptr, *d_wprof = nullptr;
   int *d_counter = nullptr; int *d_dbg = nullptr; long long watchdog_cycles = 0;
   float pass_ms[2] = {0.f, 0.f}; int n_suspends = 0;
@@ -132,7 +133,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_scenarios(ctx); free_results(ctx); free_ws(ctx);
-  free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_cell_total);
+  free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_cell_total); free_dev(ctx->d_pop_fgh);
   free_dev(ctx->d_order);
   free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1); if (ctx->evM) cudaEventDestroy(ctx->evM);
@@ -187,7 +188,7 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
     CK(ensure_dev(&ctx->d_order, &ctx->cap_order, sizeof(int32_t) * n));
     CK(cudaMemcpy(ctx->d_order, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   }
-  ctx->n = n; ctx->cost_bytes = cost_off; ctx->col_count = col_off; ctx->id_count = id_off;
+  ctx->cost_bytes = cost_off; ctx->col_count = col_off; ctx->id_count = id_off;      // ctx->n is set after the last copy succeeded
   const int n_poly = obs_off[n];
   const int n_vert = n_poly > 0 ? vert_off[n_poly] : 0;
   CK(ensure_dev(&ctx->d_scen, &ctx->cap_scen, sizeof(ScenDev) * n));
@@ -212,6 +213,7 @@ extern "C" int avp_scenarios_upload(avp_ctx *ctx, int n, const double *poses, co
     CK(cudaMemcpyAsync(ctx->d_verts, verts, sizeof(double) * 2 * n_vert, cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n = n;
   return 0;
 }
 
@@ -465,12 +467,19 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.nshot = ctx->d_nshot;
   P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.htab_stride = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
+  P.pop_fgh = nullptr;
+  if (ctx->trace_fgh && ctx->cap_pops > 0) {
+    CK(ensure_dev(&ctx->d_pop_fgh, &ctx->cap_fgh, sizeof(double) * 3 * (size_t)ctx->n * ctx->cap_pops));
+    P.pop_fgh = ctx->d_pop_fgh;
+  }
   P.hq_log = ctx->d_hq; P.work_counter = ctx->d_counter; P.dbg = getenv("AVP_HOST_TIMEOUT_S") ? ctx->d_dbg : nullptr; P.prof = ctx->d_prof; P.wprof = ctx->d_wprof;
   { const char *tpp = getenv("AVP_TRACE_POP"); P.trace_pop = tpp ? atoi(tpp) : -1; } P.watchdog_cycles = ctx->watchdog_cycles;
   P.work_list = ctx->d_order; P.n_work = ctx->n;
   PP.state = ctx->d_state; PP.ctl = ctx->d_ctl; PP.queue = ctx->d_queue; PP.q_mask = ctx->q_mask;
   PP.slot_ring = ctx->d_slot_ring; PP.slot_mask = ctx->slot_mask; PP.n_slots = ctx->ws_slots;
   { const char *qe = getenv("AVP_QUANTUM"); PP.quantum = (qe && atoi(qe) > 0) ? atoi(qe) : 512; }
+  { const char *oe = getenv("AVP_OVERFLOW_ODD"); PP.overflow_odd = (oe && atoi(oe) == 0) ? 0 : 1; }
+  { const char *fe = getenv("AVP_FORCE_YIELD"); PP.force_yield = (fe && atoi(fe) != 0) ? 1 : 0; }
   // SM pairs: only when the grid covers every SM (else the hardware's placement decides) and not switched off (AVP_SPREAD=0)
   { const char *se = getenv("AVP_SPREAD"); P.spread = (grid == ctx->n_sm * per_sm && ctx->n_sm >= 4 && !(se && atoi(se) == 0)) ? 1 : 0; }
   { const char *me = getenv("AVP_SPREAD_MAX"); PP.spread_max = me ? atoi(me) : (ctx->n_sm / 2 + ctx->n_sm / 4) * per_sm; }
@@ -516,6 +525,18 @@ extern "C" int avp_fetch_results(avp_ctx *ctx, avp_plan_summary *summaries, doub
   if (summaries) CK(cudaMemcpyAsync(summaries, ctx->d_sums, sizeof(avp_plan_summary) * n, cudaMemcpyDeviceToHost, ctx->stream));
   if (final_path) CK(cudaMemcpyAsync(final_path, ctx->d_paths, sizeof(double) * n * cap_path * 3, cudaMemcpyDeviceToHost, ctx->stream));
   if (pops && cap_pops > 0) CK(cudaMemcpyAsync(pops, ctx->d_pops, sizeof(int32_t) * n * cap_pops, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+/* f, g, h of every popped node (hybrid_a_star.py:206-216, :224-230 at the time of open_list.get()), recorded beside the pop
+ * indices of the following plans when on != 0 and cap_pops > 0; read with avp_fetch_pop_fgh */
+extern "C" int avp_trace_fgh(avp_ctx *ctx, int on) { if (!ctx) return -3; ctx->trace_fgh = on != 0; return 0; }
+extern "C" int avp_fetch_pop_fgh(avp_ctx *ctx, double *out, int cap_pops) {
+  if (!ctx) return -3;
+  if (!ctx->d_pop_fgh || !ctx->trace_fgh || cap_pops != ctx->cap_pops || !out) FAIL("avp_fetch_pop_fgh: no f/g/h trace of that size (avp_trace_fgh, then plan with cap_pops > 0)");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_pop_fgh, sizeof(double) * 3 * (size_t)ctx->n * cap_pops, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -59,6 +59,7 @@ struct KParams {
   avp_plan_summary *sums;
   double *paths; int cap_path;
   int32_t *pops; int cap_pops;
+  double *pop_fgh;                // n * cap_pops * 3: f, g, h of every popped node at the time of its pop (avp_trace_fgh), may be NULL
   int32_t *hq_log;                // n * AVP_HQ_CAP * 3, may be NULL
   int *work_counter;
   const int32_t *work_list;       // processing order (longest start-goal distance first); NULL: 0..n_work-1
@@ -462,11 +463,20 @@ __global__ void __launch_bounds__(128) k_rs_optimal(int m, const double *q, doub
 // on it the first AVP_SM_HEAP entries live in shared memory (sheap) and gheap[0 .. AVP_SM_HEAP) is their save area
 // (dij_heap_load / dij_heap_store), so a search can be suspended on one SM and resumed on another.
 
-#ifdef AVP_NO_PREFETCH      // A/B build
-__device__ __forceinline__ void prefetch_l1(const void *) { }
-#else
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// AVP_PREFETCH_MODE (A/B builds): 0 none, 1 prefetch.global.L1, 2 a load whose result is never used (default: the only mode that
+// measured faster than none, profiles/experiments_r02.md), 3 prefetch.global.L2
+#ifndef AVP_PREFETCH_MODE
+#define AVP_PREFETCH_MODE 2
 #endif
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#if AVP_PREFETCH_MODE == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif AVP_PREFETCH_MODE == 2
+  unsigned sink; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(sink) : "l"(p));
+#elif AVP_PREFETCH_MODE == 3
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 
 struct DijCtx {
   const ScenDev *S; const uint8_t *cost;
@@ -811,4 +821,7 @@ __device__ __forceinline__ void child_pose(const avp_config &cfg, const Node &cn
 enum { CTL_RUN = 0, CTL_EXIT = 1 };
 
 // shared-memory entries of the open heap per CTA width (dynamic shared memory: 12 bytes per entry)
-__host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? 2048 : 1024; }   // more shared memory here costs L1 hit rate (libm tables, nodes)
+#ifndef AVP_SMO_WIDE
+#define AVP_SMO_WIDE 2048
+#endif
+__host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? AVP_SMO_WIDE : 1024; }   // more shared memory here costs L1 hit rate (libm tables, nodes)

@@ -41,6 +41,8 @@ struct PlanParams {
   int32_t *slot_ring; int slot_mask; int n_slots;
   int quantum;                   // pops per turn while others wait
   int spread_max;                // the CTAs on odd SM ids only work while more scenarios than this are live (P.K.spread)
+  int overflow_odd;              // the CTAs on odd SM ids take searches that WAIT in the queue even while they stand back (AVP_OVERFLOW_ODD=0: off)
+  int force_yield;               // development aid: let go of the scenario at EVERY quantum end (tests of the suspend / resume path on small batches)
 };
 
 // multi-producer / multi-consumer ring of non-negative ints; at most (mask + 1) entries are ever in flight, so a cell is
@@ -208,12 +210,20 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
     //      header); if the live count has not moved for ~0.25 s they work anyway (no even CTA resident, e.g. a shared device).
     if (tid == 0) {
       int got = -1;
-      long long t_last = clock64(); int last = -1; const long long t_idle = t_last;
+      long long t_last = clock64(); int last = -1; const long long t_idle = t_last; bool seen_waiting = false; long long t_wait = 0;
       for (;;) {
         const int fin = *(volatile int *)&ctl->finalised;
         if (fin >= P.n_work) break;
         bool allowed = !(P.spread && s_odd) || (P.n_work - fin > PP.spread_max);
         if (!allowed) {
+          // standing back -- unless searches have been WAITING in the queue for ~100 us: more searches are live than there are even
+          // SMs, and a search that runs beside a busy neighbour (-25 %) beats one that does not run at all.  The odd CTA gives it
+          // back at the end of the quantum (stand_back below) and the even CTAs, which let go of theirs whenever somebody waits,
+          // pick it up within that time: the searches rotate through the shared pairs instead of staying there.
+          const bool q = (*(volatile int *)&ctl->q_head - *(volatile int *)&ctl->q_tail) < 0;
+          if (!q) seen_waiting = false;
+          else if (!seen_waiting) { seen_waiting = true; t_wait = clock64(); }
+          else if (PP.overflow_odd && clock64() - t_wait > 200000ll) allowed = true;
           if (fin != last) { last = fin; t_last = clock64(); }
           else if (clock64() - t_last > 500000000ll) allowed = true;
         }
@@ -299,12 +309,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         const int fin = *(volatile int *)&ctl->finalised;
         const bool waiting = (*(volatile int *)&ctl->q_head - *(volatile int *)&ctl->q_tail) < 0;
         const bool stand_back = P.spread && s_odd && (P.n_work - fin <= PP.spread_max);
-        if (waiting || stand_back) { s_status = AVP_PENDING; s_ctlA = CTL_EXIT; return; }
+        if (waiting || stand_back || PP.force_yield) { s_status = AVP_PENDING; s_ctlA = CTL_EXIT; return; }
         s_limit = s_npops + PP.quantum;
       }
       const int ret = s_oi[0];
       s_cur = ret;
-      if (pops && s_npops < P.cap_pops) pops[s_npops] = ret;
+      if (pops && s_npops < P.cap_pops) {
+        pops[s_npops] = ret;
+        if (P.pop_fgh) { double *o = P.pop_fgh + ((size_t)sc * P.cap_pops + s_npops) * 3; o[0] = nodes[ret].f; o[1] = nodes[ret].g; o[2] = nodes[ret].h; }
+      }
       s_npops++;
       int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_;
       s_ctlA = CTL_RUN;
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
             if (lane == 0) {
               if (hql && s_nhq < AVP_HQ_CAP) { hql[3 * s_nhq] = (int)term; hql[3 * s_nhq + 1] = d; hql[3 * s_nhq + 2] = s_D.closed_len; }
               s_nhq++;
-              if (d < 0) s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE;
+              if (d < 0) { s_status = s_D.status ? s_D.status : AVP_H_UNREACHABLE; s_nhcalls++; }      // the call was entered (hybrid_a_star.py:261); the reference never returns from it
             }
             __syncwarp();
             if (__shfl_sync(AVP_FULL_MASK, s_status, 0)) break;
@@ -903,6 +916,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       for (int i = 0; i < 4; ++i) R.boundary[i] = S.b[i];
       R.origin[0] = S.b[0]; R.origin[1] = S.b[2];
       R.n_astar = 0; R.n_rs = 0; R.n_final = 0; R.rs_nseg = 0; R.rs_L = 0.0;
+      if (s_cur >= 0 && slot >= 0) { R.last_pose[0] = nodes[s_cur].x; R.last_pose[1] = nodes[s_cur].y; R.last_pose[2] = nodes[s_cur].theta; }
+      else { R.last_pose[0] = 0.0; R.last_pose[1] = 0.0; R.last_pose[2] = 0.0; }
       for (int i = 0; i < 5; ++i) R.rs_lengths[i] = 0.0;
       for (int i = 0; i < 8; ++i) R.rs_ctypes[i] = 0;
       if (status == AVP_OK || status == AVP_OPEN_EXHAUSTED_RS) {

@@ -40,7 +40,7 @@ class AvpPlanSummary(ctypes.Structure):
         ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("n_obs", ctypes.c_int32), ("n_hcalls", ctypes.c_int32),
         ("rs_L", ctypes.c_double), ("rs_lengths", ctypes.c_double * AVP_MAX_RS_SEG),
         ("rs_ctypes", ctypes.c_char * 8), ("origin", ctypes.c_double * 2), ("pitch", ctypes.c_double * 2),
-        ("boundary", ctypes.c_double * 4),
+        ("boundary", ctypes.c_double * 4), ("last_pose", ctypes.c_double * 3),
     ]
 
 
@@ -52,7 +52,7 @@ SUMMARY_DTYPE = np.dtype([
     ("n_astar", "<i4"), ("n_rs", "<i4"), ("n_final", "<i4"), ("rs_nseg", "<i4"), ("last_index", "<i4"),
     ("n_hq", "<i4"), ("h_closed", "<i4"), ("nx", "<i4"), ("ny", "<i4"), ("n_obs", "<i4"), ("n_hcalls", "<i4"),
     ("rs_L", "<f8"), ("rs_lengths", "<f8", (AVP_MAX_RS_SEG,)), ("rs_ctypes", "S8"),
-    ("origin", "<f8", (2,)), ("pitch", "<f8", (2,)), ("boundary", "<f8", (4,)),
+    ("origin", "<f8", (2,)), ("pitch", "<f8", (2,)), ("boundary", "<f8", (4,)), ("last_pose", "<f8", (3,)),
 ])
 assert SUMMARY_DTYPE.itemsize == ctypes.sizeof(AvpPlanSummary)
 

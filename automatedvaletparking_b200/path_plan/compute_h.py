@@ -41,6 +41,10 @@ class _ClosedList:
 
 
 class Dijkstra:
+    """Every Dijkstra object owns its queue, closed list and h table, like the reference's: the first object on a Map uses the
+    Map's device context, any further one (and any object made after that context ran a whole search, which re-uses the
+    per-cell arrays) gets a context of its own."""
+
     def __init__(self, map: Map) -> None:
         self.map = map
         self.final_point = (map.case.xf, map.case.yf, map.case.thetaf)
@@ -50,14 +54,31 @@ class Dijkstra:
         self._hv = None
         self.closedlist = _ClosedList(self)
         self.terminate_grid_id = None
+        owner = getattr(map, "_dijkstra_owner", None)
+        if owner is None or owner() is None:
+            import weakref
+            self._dev = map._device
+            map._dijkstra_owner = weakref.ref(self)
+        else:
+            from ..batch import DevicePlanner
+            from ..hostcfg import default_config
+            cfg = dict(default_config())
+            cfg['map_discrete_size'] = map.discrete_size
+            self._dev = DevicePlanner(cfg, device=getattr(map._device, "device", 0))
+            self._dev.load([map.scenario])
+        self._epoch = self._dev.plan_epoch
 
     def _hvalues(self):
         if self._hv is None:
-            self._hv = self.map._device.hvalues(0)
+            self._hv = self._dev.hvalues(0)
         return self._hv
 
     def compute_path(self, node_x, node_y):
-        d, closed, term = self.map._device.dijkstra_query(0, float(node_x), float(node_y), reset=self._fresh)
+        if self._dev.plan_epoch != self._epoch and not self._fresh:
+            raise RuntimeError("this Dijkstra object's device state was overwritten by a whole search on the same context "
+                               "(PathPlanner.a_star_plan); create the Dijkstra object after planning, or plan on another Map")
+        d, closed, term = self._dev.dijkstra_query(0, float(node_x), float(node_y), reset=self._fresh)
+        self._epoch = self._dev.plan_epoch
         self._fresh = False
         self._hv = None
         self._closed_len = closed

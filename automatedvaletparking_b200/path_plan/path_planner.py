@@ -94,13 +94,14 @@ class PathPlanner:
         n_astar, n_rs = int(s['n_astar']), int(s['n_rs'])
         a_star_path = [[np.float64(p[0]), np.float64(p[1]), np.float64(p[2])] for p in path[:n_astar]]
         final_path = copy.deepcopy(a_star_path) + [[float(p[0]), float(p[1]), float(p[2])] for p in path[n_astar:]]
-        # the PATH object of the successful shot: word, lengths and course (course from the device path rows)
-        last = path[n_astar - 1]
+        # the PATH object of the successful shot: word, lengths and course.  Point 0 of the course is the popped node's own pose
+        # (rs_curve.py:118-132) -- not the last finish_path row, which is re-rolled with 3 * ddt != dt and can differ in the last bit
+        lp = [float(v) for v in s['last_pose']]
         nseg = int(s['rs_nseg'])
-        rs_x = [float(last[0])] + [float(p[0]) for p in path[n_astar:]]
-        rs_y = [float(last[1])] + [float(p[1]) for p in path[n_astar:]]
-        rs_yaw = [float(last[2])] + [float(p[2]) for p in path[n_astar:]]
-        full = rs_curve.calc_optimal_path(a_star_path[-1][0], a_star_path[-1][1], a_star_path[-1][2] if n_astar > 1 else float(last[2]),
+        rs_x = [lp[0]] + [float(p[0]) for p in path[n_astar:]]
+        rs_y = [lp[1]] + [float(p[1]) for p in path[n_astar:]]
+        rs_yaw = [lp[2]] + [float(p[2]) for p in path[n_astar:]]
+        full = rs_curve.calc_optimal_path(np.float64(lp[0]), np.float64(lp[1]), np.float64(lp[2]) if int(s['last_index']) != 0 else lp[2],
                                           self.map.case.xf, self.map.case.yf, rs_curve.pi_2_pi(self.map.case.thetaf), 1 / self.vehicle.min_radius_turn)
         rs_path = PATH([float(v) for v in s['rs_lengths'][:nseg]], list(s['rs_ctypes'].decode()), float(s['rs_L']), rs_x, rs_y, rs_yaw,
                        full.directions if len(full.directions) == n_rs else [0] * n_rs)

@@ -87,6 +87,7 @@ typedef struct avp_plan_summary {
   double origin[2];        /* (boundary[0], boundary[2]): origin of the fp32 relative path copy */
   double pitch[2];         /* _discrete_x, _discrete_y */
   double boundary[4];
+  double last_pose[3];     /* x, y, theta of the last popped node: point 0 of rs_path (rs_curve.py:118-132) */
 } avp_plan_summary;
 
 typedef struct avp_ctx avp_ctx;
@@ -191,6 +192,12 @@ int avp_fetch_hvalues(avp_ctx *ctx, int s, int32_t *hval, int64_t cap, int64_t *
  * closed_len = len(closedlist), target_id = terminate_grid_id.  The h table is read with
  * avp_fetch_hvalues.  A plan run reuses the per-id arrays and invalidates this state. */
 int avp_dijkstra_query(avp_ctx *ctx, int s, int reset, double node_x, double node_y, int32_t *dist, int32_t *closed_len, int32_t *target_id);
+
+/* parity aid for calc_node_cost / calc_node_heuristic (hybrid_a_star.py:243-298): with on != 0 the following plans record f, g, h
+ * of every popped node as they are at open_list.get() (path_planner.py:70), beside the pop indices (needs cap_pops > 0);
+ * avp_fetch_pop_fgh copies them out: out[n][cap_pops][3]. */
+int avp_trace_fgh(avp_ctx *ctx, int on);
+int avp_fetch_pop_fgh(avp_ctx *ctx, double *out, int cap_pops);
 
 /* replaces PathPlanner.split_path (path_planner.py:112-192): gear-change detection (scipy.spatial.distance.cosine semantics,
  * NaN for a zero displacement) and the collision-checked extension points, for every finished plan of the batch (results of

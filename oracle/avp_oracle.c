@@ -979,6 +979,7 @@ int orc_plan(const orc_map *m, const avp_config *cfg, orc_plan_out *out) {
 done:
   S->status = A.status; S->global_index = A.global_index; S->n_closed = A.n_closed; S->n_open = A.hn;
   S->n_hq = A.n_hq; S->h_closed = (int32_t)A.dij->closed_len; S->n_hcalls = A.n_hcalls;
+  if (S->last_index >= 0 && S->n_pops > 0) { const onode *ln = &A.nodes[S->last_index]; S->last_pose[0] = ln->x; S->last_pose[1] = ln->y; S->last_pose[2] = ln->theta; }
   if (out->hval_out) for (long i = 0; i < A.dij->n_ids && i < out->hval_cap; ++i) out->hval_out[i] = A.dij->hval[i];
   orc_dij_free(A.dij); free(A.nodes); free(A.heap); free(A.htab); free(A.rsbuf); free(rsp);
   return 0;

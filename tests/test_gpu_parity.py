@@ -338,3 +338,96 @@ def test_config4_synthetic_batch_vs_oracle(device_planner, cfg):
     res = dp.plan(cap_path=512, cap_pops=0)
     assert (res.summaries["nx"] == 200).all() and (res.summaries["n_obs"] > 1000).all()
     _compare_many(res, scs, _oracle_many(scs, cfg))
+
+
+def test_popped_nodes_f_g_h_bit_exact(device_planner, cfg):
+    """calc_node_cost / calc_node_heuristic (hybrid_a_star.py:243-298) checked directly: f, g, h of every popped node as they
+    are at open_list.get(), against the oracle and against the reference's own traces (tests/golden/cases pop_fgh)."""
+    dp = device_planner
+    cases = (1, 4, 5, 13, 16, 17)
+    scs = [scn.benchmark_case(c) for c in cases] + scn.perturbed_set(scn.benchmark_case(9), 3, seed=109)
+    dp.load(scs)
+    dp.trace_fgh(True)
+    try:
+        res = dp.plan(cap_path=512, cap_pops=4096)
+        fgh = dp.pop_fgh(4096)
+    finally:
+        dp.trace_fgh(False)
+    for k, sc in enumerate(scs):
+        r = O.plan(O.OracleMap(sc), cfg)
+        n = min(int(res.summaries["n_pops"][k]), 4096)
+        assert n == min(r["n_pops"], 4096) and np.array_equal(fgh[k, :n], r["pop_fgh"][:n]), sc.name
+        g = os.path.join(GOLDEN, "cases", f"{sc.name}.npz")
+        if os.path.exists(g):
+            ref = np.load(g)["pop_fgh"]
+            m = min(len(ref), n)
+            assert np.array_equal(fgh[k, :m], ref[:m]), sc.name
+
+
+def test_config3_full_size_vs_oracle(device_planner, cfg):
+    """BASELINE configs[2] at FULL size: 20 cases x 256 collision-free perturbations = 5120 scenarios (the bench recipe), every
+    summary field and every returned path against the oracle."""
+    import bench
+    dp = device_planner
+    scs = bench.make_c3(dp)
+    assert len(scs) == 5120
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=0)
+    _compare_many(res, scs, _oracle_many(scs, cfg))
+    assert int((res.summaries["status"] == 5).sum()) >= 3 * 200          # Cases 7, 8, 19 never finish
+
+
+def test_config4_full_size_vs_oracle(device_planner, cfg):
+    """BASELINE configs[3] at FULL size: 64 synthetic maps x 64 start/goal pairs = 4096 scenarios (status parity: at this obstacle
+    density every search ends at its first pop)."""
+    import bench
+    dp = device_planner
+    scs = bench.make_c4(dp)
+    assert len(scs) == 4096
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=0)
+    _compare_many(res, scs, _oracle_many(scs, cfg))
+
+
+def test_root_expansion_boundary_rule_matches_oracle(device_planner, cfg):
+    """closed_list is re-read for every successor (hybrid_a_star.py:155-163): in the ROOT expansion an earlier sibling that collides
+    switches the boundary test on for the later ones.  Tight boundary overrides around the start pose make that visible."""
+    dp = device_planner
+    base = scn.benchmark_case(1)
+    rng = np.random.default_rng(11)
+    scs = []
+    for i in range(96):
+        x0, y0 = base.x0 + rng.uniform(-1, 1), base.y0 + rng.uniform(-1, 1)
+        pad = rng.uniform(0.2, 2.5, size=4)
+        b = (float(np.floor(min(x0, base.xf) - 12)), float(x0 + pad[1]), float(np.floor(min(y0, base.yf) - 12)), float(y0 + pad[3]))
+        scs.append(scn.Scenario(float(x0), float(y0), float(rng.uniform(-np.pi, np.pi)), base.xf, base.yf, base.thetaf, base.obs, b, f"tight{i}"))
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=20000)
+    n_diff = 0
+    for k, sc in enumerate(scs):
+        r = _compare_plan(dp, res, k, sc, cfg)
+        n_diff += r["n_closed"] > 0
+    assert n_diff > 10
+
+
+@pytest.mark.parametrize("env", [
+    {"AVP_QUANTUM": "7", "AVP_FORCE_YIELD": "1"},                                   # every search is let go of every 7 pops and resumed (often on another SM)
+    {"AVP_QUANTUM": "5", "AVP_FORCE_YIELD": "1", "AVP_SLOTS": "3"},                 # ... with a slot pool that runs dry: fresh scenarios go to the back of the queue
+    {"AVP_QUANTUM": "16", "AVP_FORCE_YIELD": "1", "AVP_PLAN_BLOCK": "256"},         # two 256-thread CTAs per SM
+    {"AVP_QUANTUM": "64", "AVP_SPREAD": "0"},
+])
+def test_results_do_not_depend_on_the_scheduling(device_planner, cfg, monkeypatch, env):
+    """Suspend / resume (run queue, slot pool, save areas of the heap heads), CTA width and SM-pair placement are scheduling only:
+    pops, traces and paths of the benchmark cases and of a perturbed batch stay bit-identical to the oracle."""
+    dp = device_planner
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    scs = [scn.benchmark_case(i) for i in (1, 2, 4, 5, 9, 13, 16, 17, 20)] + scn.perturbed_set(scn.benchmark_case(3), 6, seed=103)
+    dp.load(scs)
+    res = dp.plan(cap_path=512, cap_pops=8192)
+    _, _, n_suspend, block = dp.last_search_passes()
+    for k, sc in enumerate(scs):
+        _compare_plan(dp, res, k, sc, cfg)
+    if "AVP_FORCE_YIELD" in env:
+        assert n_suspend > 100
+    assert block == int(env.get("AVP_PLAN_BLOCK", 512))
