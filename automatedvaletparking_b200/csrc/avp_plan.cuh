@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
   __shared__ __align__(8) unsigned long long s_cell_bar;       // mbarrier of the staged cell list
   unsigned char *s_cells = s_dyn + 12 * SMO;                   // AVP_CELL_SMEM bytes: double2 cells, then the int32 column starts
   unsigned cell_parity = 0;
-  LPROF(__shared__ long long s_lp[4]; __shared__ long long s_lpe, s_lpc;)
+  LPROF(__shared__ long long s_lp[8]; __shared__ long long s_lpe, s_lpc, s_lpt;)
 #ifdef AVP_PROFILE
   __shared__ int s_trace_on;
   __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts)
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
     PROF(if (tid == 32) tp = clock_ordered();)
 
     bool reached = false;
-    LPROF(if (tid < 4) s_lp[tid] = 0; if (tid == 32) s_lpe = clock_ordered(); if (tid == 0) s_lpc = clock_ordered();)
+    LPROF(if (tid < 8) s_lp[tid] = 0; if (tid == 32) s_lpe = clock_ordered(); if (tid == 0) s_lpc = clock_ordered();)
     for (;;) {
       __syncthreads();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
       LPROF(if (tid == 32) { const long long t_ = clock_ordered(); s_lp[0] += t_ - s_lpe; s_lpe = t_; } if (tid == 0) { s_lp[2] += clock_ordered() - s_lpc; s_lp[3] += 1; })
@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       TS(1);
       __syncthreads();                                 // ---- barrier B: target published
       LPROF(if (tid == 32) { s_lp[1] += clock_ordered() - s_lpe; })
+      LPROF(if (tid == 0) s_lpt = clock_ordered();)
       TS(2);
       PIPE_TICK(32, 15);                         // evaluators waiting for the target
       if (s_ctlB != CTL_RUN) { reached = (s_ctlB == CTL_FINISH); break; }
@@ -531,6 +532,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
           __syncwarp();
         }
         if (lane == 0) { __threadfence_block(); st_release_cta(&s_ins_done, 1); }      // the evaluators may probe the table now
+        LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[4] += t_ - s_lpt; s_lpt = t_; })
         if (s_do_commit && s_status == 0) {
           const PureRes &R = s_res[s_rb];
           const int cur = s_cur;
@@ -581,7 +583,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
             // heuristic miss for successor `stop`: Dijkstra.compute_path resumes (compute_h.py:198-214)
             long long term;
             PROF(const long long td_ = clock64();)
+            LPROF(long long tdl_ = 0; if (tid == 0) tdl_ = clock_ordered();)
             const int d = dij_compute_path(s_D, s_heap, R.cpose[stop][0], R.cpose[stop][1], &term);
+            LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[6] += t_ - tdl_; s_lpt += t_ - tdl_; })
             PROF(if (lane == 0) { pc[10] += clock64() - td_; pc[11]++; })
             ++n_miss;
             if (lane == 0) {
@@ -599,7 +603,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         WP_ACC(1);
         TS(3);
         PIPE_TICK(0, 2);                         // node records + sequential commit
+        LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[5] += t_ - s_lpt; s_lpt = t_; })
         if (lane == 0 && (s_do_commit || s_status != 0)) do_pop();
+        LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[7] += t_ - s_lpt; s_lpt = t_; })
         WP_ACC(2);
         TS(4);
         PIPE_TICK(0, 3);                         // heappop
@@ -878,7 +884,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       }
     }
     __syncthreads();
-    LPROF(if (tid < 4 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
+    LPROF(if (tid < 8 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
 #ifdef AVP_PROFILE
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] += s_wp[warp][k]; }
     if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_ic[tid];

@@ -140,7 +140,8 @@ def _compare_plan(dp, res, k, sc, cfg, ref=None):
     s = res.summaries[k]
     for key in ("status", "n_pops", "global_index", "n_closed", "n_open", "n_astar", "n_rs", "n_final", "n_hq", "h_closed", "n_hcalls"):
         assert int(s[key]) == r[key], (sc.name, key, int(s[key]), r[key])
-    assert np.array_equal(res.pop_indices(k), r["pops"]), sc.name                  # expanded-node indices
+    gp = res.pop_indices(k)                                                        # expanded-node indices (n_pops itself is compared above;
+    assert np.array_equal(gp, r["pops"][:len(gp)]) and len(gp) == min(r["n_pops"], res.pops.shape[1]), sc.name   # the trace is capped at cap_pops)
     hq = dp.hq_log(k, int(s["n_hq"]))
     assert np.array_equal(hq, r["hq"][:len(hq)].astype(np.int32)), sc.name         # Dijkstra query trace
     if r["status"] in (0, 2):

@@ -24,6 +24,10 @@ for nm, idx in (("long (20000 pops)", np.where(s["n_pops"] >= 20000)[0]), ("mid 
     if len(idx) == 0:
         continue
     pops = np.maximum(pr[idx, 3], 1.0)
-    print("%-18s n %4d pops/scenario %8.1f | per pop: evaluators wait at A %7.0f | serial section A->B %7.0f | commit warp waits at A %7.0f" %
-          (nm, len(idx), s["n_pops"][idx].mean(), (pr[idx, 0] / pops).mean(), (pr[idx, 1] / pops).mean(), (pr[idx, 2] / pops).mean()))
+    print("%-18s n %4d pops/scenario %8.1f | per pop: evaluators wait at A %7.0f | serial section A->B %7.0f | commit warp waits at A %7.0f"
+          " | commit warp: records+inserts %6.0f  commit loop %6.0f  Dijkstra %6.0f  heappop %6.0f" %
+          (nm, len(idx), s["n_pops"][idx].mean(), (pr[idx, 0] / pops).mean(), (pr[idx, 1] / pops).mean(), (pr[idx, 2] / pops).mean(),
+           (pr[idx, 4] / pops).mean(), (pr[idx, 5] / pops).mean(), (pr[idx, 6] / pops).mean(), (pr[idx, 7] / pops).mean()))
+    tot = float(s["n_pops"][idx].sum())
+    print("%-18s total pops %.0f" % ("", tot))
 dp.close()
