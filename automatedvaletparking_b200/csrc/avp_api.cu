@@ -94,13 +94,13 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return -8; }
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
-  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(512) + AVP_CELL_SMEM);
-  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(256) + AVP_CELL_SMEM);
-  cudaFuncSetAttribute(k_plan<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * avp_sm_open(640) + AVP_CELL_SMEM);
+  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(512));
+  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(256));
+  cudaFuncSetAttribute(k_plan<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(640));
   {
     int o = 0;
-    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, 12 * avp_sm_open(512) + AVP_CELL_SMEM) == cudaSuccess && o > 0) ? o : 1;
-    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, 12 * avp_sm_open(256) + AVP_CELL_SMEM) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, AVP_PLAN_DYN_SMEM(512)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, AVP_PLAN_DYN_SMEM(256)) == cudaSuccess && o > 0) ? o : 1;
   }
   ctx->slots = ctx->n_sm * ctx->ctas_per_sm[0];               // persistent grids: multiples of the SM count
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evM);
@@ -495,9 +495,9 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
     k_dij_eager<<<dgrid, AVP_DIJ_WARPS * 32, 0, ctx->stream>>>(PP); ctx->launches++;
   }
   CK(cudaEventRecord(ctx->evM, ctx->stream));
-  if (block == 512) k_plan<512><<<grid, 512, 12 * avp_sm_open(512) + AVP_CELL_SMEM, ctx->stream>>>(PP);
-  else if (block == 640) k_plan<640><<<grid, 640, 12 * avp_sm_open(640) + AVP_CELL_SMEM, ctx->stream>>>(PP);
-  else k_plan<256><<<grid, 256, 12 * avp_sm_open(256) + AVP_CELL_SMEM, ctx->stream>>>(PP);
+  if (block == 512) k_plan<512><<<grid, 512, AVP_PLAN_DYN_SMEM(512), ctx->stream>>>(PP);
+  else if (block == 640) k_plan<640><<<grid, 640, AVP_PLAN_DYN_SMEM(640), ctx->stream>>>(PP);
+  else k_plan<256><<<grid, 256, AVP_PLAN_DYN_SMEM(256), ctx->stream>>>(PP);
   ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());

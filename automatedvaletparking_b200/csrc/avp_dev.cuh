@@ -416,17 +416,25 @@ __device__ __forceinline__ bool rs_SLS(double x, double y, double phi, double &t
   }
   return false;
 }
+// The word formulas below evaluate R(x, y) = (hypot, atan2) lazily: a result the reference computes but whose value cannot
+// reach the output (the branch is not taken, or the value is never read) is not evaluated.  hypot and atan2 are pure, so this
+// is exact.  atan2(Y, X) < 0 for every Y < 0 that is not so small that the quotient underflows to -0.0 (-0.0 >= 0.0 is true in
+// the reference): the sign tests below only trust Y < -1e-100.
 // rs_curve.py:159-167
 __device__ __forceinline__ bool rs_LSL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
-  double uu, tt; rs_R(x - sphi, y - 1.0 + cphi, uu, tt);
-  if (tt >= 0.0) { const double vv = rs_M(phi - tt); if (vv >= 0.0) { t = tt; u = uu; v = vv; return true; } }
+  const double X = x - sphi, Y = y - 1.0 + cphi;
+  if (Y < -1e-100) return false;                                   // t = atan2(Y, X) < 0
+  const double tt = d_atan2(Y, X);
+  if (tt >= 0.0) { const double vv = rs_M(phi - tt); if (vv >= 0.0) { t = tt; u = py_hypot(X, Y); v = vv; return true; } }
   return false;
 }
 // rs_curve.py:170-183
 __device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
-  double u1, t1; rs_R(x + sphi, y - 1.0 - cphi, u1, t1);
+  const double X = x + sphi, Y = y - 1.0 - cphi;
+  double u1 = py_hypot(X, Y);
   u1 = d_pow2(u1);                                                 // u1 ** 2 == libm pow(u1, 2.0)
   if (u1 >= 4.0) {
+    const double t1 = d_atan2(Y, X);
     const double uu = sqrt(u1 - 4.0), theta = d_atan2(2.0, uu), tt = rs_M(t1 + theta), vv = rs_M(tt - phi);
     if (tt >= 0.0 && vv >= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
@@ -434,8 +442,10 @@ __device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double sp
 }
 // rs_curve.py:186-197
 __device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
-  double u1, t1; rs_R(x - sphi, y - 1.0 + cphi, u1, t1);
+  const double X = x - sphi, Y = y - 1.0 + cphi;
+  const double u1 = py_hypot(X, Y);
   if (u1 <= 4.0) {
+    const double t1 = d_atan2(Y, X);
     const double uu = -2.0 * d_asin(0.25 * u1), tt = rs_M(t1 + 0.5 * uu + AVP_PI), vv = rs_M(phi - tt + uu);
     if (tt >= 0.0 && uu <= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
@@ -472,8 +482,11 @@ __device__ __forceinline__ bool rs_LRLRp(double x, double y, double phi, double 
 }
 // rs_curve.py:391-403
 __device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
-  const double xi = x + sphi, eta = y - 1.0 - cphi; double rho, theta; rs_R(-eta, xi, rho, theta);
+  const double xi = x + sphi, eta = y - 1.0 - cphi;
+  if (xi < -1e-100) return false;                                  // t = theta = atan2(xi, -eta) < 0
+  const double rho = py_hypot(-eta, xi);
   if (rho >= 2.0) {
+    const double theta = d_atan2(xi, -eta);
     const double tt = theta, uu = 2.0 - rho, vv = rs_M(tt + 0.5 * AVP_PI - phi);
     if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
@@ -481,16 +494,19 @@ __device__ __forceinline__ bool rs_LRSR(double x, double y, double phi, double s
 }
 // rs_curve.py:406-419
 __device__ __forceinline__ bool rs_LRSL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
-  const double xi = x - sphi, eta = y - 1.0 + cphi; double rho, theta; rs_R(xi, eta, rho, theta);
+  const double xi = x - sphi, eta = y - 1.0 + cphi;
+  const double rho = py_hypot(xi, eta);
   if (rho >= 2.0) {
+    const double theta = d_atan2(eta, xi);
     const double r = sqrt(rho * rho - 4.0), uu = 2.0 - r, tt = rs_M(theta + d_atan2(r, -2.0)), vv = rs_M(phi - 0.5 * AVP_PI - tt);
     if (tt >= 0.0 && uu <= 0.0 && vv <= 0.0) { t = tt; u = uu; v = vv; return true; }
   }
   return false;
 }
-// rs_curve.py:494-510
+// rs_curve.py:494-510 (theta of R(xi, eta) is computed by the reference and never read)
 __device__ __forceinline__ bool rs_LRSLR(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
-  const double xi = x + sphi, eta = y - 1.0 - cphi; double rho, theta; rs_R(xi, eta, rho, theta);
+  const double xi = x + sphi, eta = y - 1.0 - cphi;
+  const double rho = py_hypot(xi, eta);
   if (rho >= 2.0) {
     const double uu = 4.0 - sqrt(rho * rho - 4.0);
     if (uu <= 0.0) {
@@ -563,6 +579,10 @@ struct RsCand { double t, u, v, L; };   // L = sum(|lengths|) of the arranged wo
 
 struct RsBest { int ok; int degenerate; int n; int ct; double len[5]; double L; /* normalised */ int inst; /* winning word instance */ };
 
+// The same with the arranged word kept (k_plan): the selection reads lengths / ctype / np-type mask instead of re-deriving them
+// with rs_arrange for every comparison (88 k warp-cycles per pop in round 1's profile).
+struct RsCandX { double t, u, v, L; double len[5]; int32_t n, ct; uint32_t mask; int32_t pad; };
+
 // instances that can share a ctype form 11 groups (same family pair), in instance order
 __device__ __constant__ int8_t rs_grp_begin[12] = {0, 1, 2, 6, 10, 18, 26, 30, 34, 38, 42, 46};
 #define RS_NGROUP 11
@@ -597,6 +617,33 @@ __device__ __forceinline__ void rs_select_group(const RsCand *cand, unsigned lon
     }
     if (dup) continue;
     const double L = cand[inst].L;
+    if (L >= 1000.0) continue;                                    // MAX_LENGTH
+    if (!(L >= 0.01)) { out.degenerate = 1; continue; }           // assert (rs_curve.py:153)
+    retained |= (1ull << inst);
+    const double Lm = L / maxc;
+    if (out.inst < 0 || Lm <= out.Lm) { out.inst = inst; out.Lm = Lm; }     // last <= wins
+  }
+}
+
+// rs_select_group on candidates that carry their arranged word
+__device__ __forceinline__ void rs_select_group_x(const RsCandX *cand, unsigned long long valid, int g, double maxc, RsGroupBest &out) {
+  unsigned long long retained = 0ull;
+  out.inst = -1; out.degenerate = 0; out.Lm = 0.0;
+  const int beg = rs_grp_begin[g], end = rs_grp_begin[g + 1];
+  for (int inst = beg; inst < end; ++inst) {
+    if (!((valid >> inst) & 1ull)) continue;
+    const RsCandX &c = cand[inst];
+    bool dup = false;
+    for (int e = beg; e < inst; ++e) {
+      if (!((retained >> e) & 1ull)) continue;
+      const RsCandX &o = cand[e];
+      if (o.ct != c.ct) continue;
+      double d[5];
+      for (int i = 0; i < c.n; ++i) d[i] = o.len[i] - c.len[i];
+      if (py_sum(d, c.n, c.mask) <= 0.01) { dup = true; break; }     // rs_curve.py:143-146
+    }
+    if (dup) continue;
+    const double L = c.L;
     if (L >= 1000.0) continue;                                    // MAX_LENGTH
     if (!(L >= 0.01)) { out.degenerate = 1; continue; }           // assert (rs_curve.py:153)
     retained |= (1ull << inst);

@@ -606,11 +606,25 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
     // the popped cell is expanded next: its neighbours' state words and cost-map bytes are prefetched while lane 0 sifts (the
     // positions are estimated from the id -- ids and raster indices are floors of the same lattice coordinates; a wrong guess
     // only costs the prefetch)
-    if (lane >= 1 && lane <= 6) {
-      const int i1 = cur_id / stride, i0 = cur_id - i1 * stride;
-      if (lane <= 3) { const int q = (i1 + lane - 2) * stride + i0 - 1; if (q >= 0 && q + 2 < n_ids) { prefetch_l1(&ost[q]); prefetch_l1(&ost[q + 2]); } }
-      else { const int xi = i0 - 1 + (lane - 5), yi = my - i1 - 3; if (xi >= 0 && xi < nx && yi >= 0 && yi + 2 < ny) { prefetch_l1(&cost[(size_t)xi * ny + yi]); prefetch_l1(&cost[(size_t)xi * ny + yi + 2]); } }
+    // ... and one pop further ahead: the root after this pop is (almost always) one of the root's two children, so their lattice
+    // coordinates and their neighbourhoods are prefetched as well (lanes 8..21)
+    {
+      int pid = -1, role = 0;
+      if (lane >= 1 && lane <= 6) { pid = cur_id; role = lane; }
+#ifndef AVP_NO_DIJ_AHEAD     // A/B build
+      else if (lane >= 8 && lane <= 14 && hn > 1) { pid = (int)(unsigned)sheap[1]; role = lane - 8; }
+      else if (lane >= 15 && lane <= 21 && hn > 2) { pid = (int)(unsigned)sheap[2]; role = lane - 15; }
+#endif
+      if (pid >= 0 && pid < n_ids) {
+        if (role == 0) { prefetch_l1(&gxa[pid]); prefetch_l1(&gya[pid]); }
+        else {
+          const int i1 = pid / stride, i0 = pid - i1 * stride;
+          if (role <= 3) { const int q = (i1 + role - 2) * stride + i0 - 1; if (q >= 0 && q + 2 < n_ids) { prefetch_l1(&ost[q]); prefetch_l1(&ost[q + 2]); } }
+          else { const int xi = i0 - 1 + (role - 5), yi = my - i1 - 3; if (xi >= 0 && xi < nx && yi >= 0 && yi + 2 < ny) { prefetch_l1(&cost[(size_t)xi * ny + yi]); prefetch_l1(&cost[(size_t)xi * ny + yi + 2]); } }
+        }
+      }
     }
+#ifdef AVP_DIJ_SERIAL_POP       // A/B build: the serial sift of round 1
     if (lane == 0) {
       const unsigned long long item = HP_GET(hn - 1);
       const int n = hn - 1;
@@ -630,6 +644,55 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
         }
         HP_SET(pos, item);
       }
+    }
+#else
+    // heapq.heappop: the last entry replaces the root and _siftup moves the smaller child up, level by level, to a leaf.  Which child
+    // is smaller depends on the heap only, not on the item, so FIVE levels are walked at once: the 31 sibling pairs below the
+    // current position are compared by 31 lanes (one load round), a ballot holds every outcome, and the path is read off it with
+    // bit operations; the lanes on the path move their winner up.  Same compares, same moves as the serial loop.
+    {
+      const int n = hn - 1;
+      unsigned long long item = 0ull;
+      if (lane == 0) item = HP_GET(n);
+      if (n > 0) {
+        int pos = 0;
+        for (;;) {
+          const int d = 32 - __clz(lane + 1), q = lane + 1 - (1 << (d - 1));          // lane -> pair q of level d (lane 31: none)
+          const long long L = (((long long)pos + 1) << d) - 1 + 2 * q;
+          const bool have = lane < 31 && L < n, have_r = have && L + 1 < n;
+          unsigned long long lv = 0ull, rv = 0ull;
+          if (have) lv = HP_GET((int)L);
+          if (have_r) rv = HP_GET((int)L + 1);
+          const bool right = have_r && !(lv < rv);
+          const unsigned long long cv = right ? rv : lv;
+          const unsigned vm = __ballot_sync(AVP_FULL_MASK, have), rm = __ballot_sync(AVP_FULL_MASK, right);
+          int node = pos, qq = 0, depth = 0, my_parent = -1;
+#pragma unroll
+          for (int dd = 1; dd <= 5; ++dd) {
+            const int lid = (1 << (dd - 1)) - 1 + qq;
+            if (depth != dd - 1 || !((vm >> lid) & 1u)) break;
+            if (lid == lane) my_parent = node;                                          // this lane's pair hangs below the path
+            const int r = (rm >> lid) & 1u;
+            node = (int)((((long long)pos + 1) << dd) - 1 + 2 * qq + r); qq = 2 * qq + r; depth = dd;
+          }
+          if (my_parent >= 0) HP_SET(my_parent, cv);
+          __syncwarp();
+          pos = node;
+          if (depth < 5) break;                                                          // a leaf
+        }
+        if (lane == 0) {
+          while (pos > 0) {                     // heapq._siftdown(heap, 0, pos)
+            const int parent = (pos - 1) >> 1;
+            const unsigned long long pv = HP_GET(parent);
+            if (item < pv) { HP_SET(pos, pv); pos = parent; continue; }
+            break;
+          }
+          HP_SET(pos, item);
+        }
+      }
+    }
+#endif
+    if (lane == 0) {
       const int id = (int)(unsigned)top;
       ost[id] = -2;
       // closedlist: the first entry per id wins (hybrid_a_star.py:272-283).  Only the goal cell is ever closed twice
@@ -795,6 +858,46 @@ __device__ __forceinline__ void oh_pop_fix(double *sf, int32_t *si, OEnt *ge, No
     OH_SET(pos, cf, ci); pos = child; child = 2 * pos + 1;
   }
   oh_siftdown<SMO>(sf, si, ge, nodes, pos, fi, item);
+}
+// (A/B build -DAVP_WARP_POP; measured 2-3 % SLOWER than the serial oh_pop_fix with prefetches on the bench workload: 62 scattered
+// 16-byte loads per round instead of 2 -- profiles/experiments_r02.md)
+// heapq.heappop after the root has been read, WARP-COLLECTIVE: five levels of _siftup per round (see dij_compute_path): the 31 sibling
+// pairs below the position are loaded and compared by 31 lanes at once -- below the shared-memory head that is ONE DRAM round trip
+// for five levels instead of five --, the path is read off the ballot, the lanes on the path move their winner up.  The final
+// _siftdown (the moved item bubbling up) is lane 0's.
+template <int SMO>
+__device__ __forceinline__ void oh_pop_fix_warp(double *sf, int32_t *si, OEnt *ge, Node *nodes, int n_before, int lane) {
+  const int last = n_before - 1;
+  double fi = 0.0; int item = 0;
+  if (lane == 0) oh_get<SMO>(sf, si, ge, last, fi, item);
+  if (last == 0) return;
+  int pos = 0;
+  for (;;) {
+    const int d = 32 - __clz(lane + 1), q = lane + 1 - (1 << (d - 1));
+    const long long L = (((long long)pos + 1) << d) - 1 + 2 * q;
+    const bool have = lane < 31 && L < last, have_r = have && L + 1 < last;
+    double lf = 0.0, rf = 0.0; int li = 0, ri = 0;
+    if (have) oh_get<SMO>(sf, si, ge, (int)L, lf, li);
+    if (have_r) oh_get<SMO>(sf, si, ge, (int)L + 1, rf, ri);
+    const bool right = have_r && !(lf < rf);
+    const double cf = right ? rf : lf; const int ci = right ? ri : li;
+    const unsigned vm = __ballot_sync(AVP_FULL_MASK, have), rm = __ballot_sync(AVP_FULL_MASK, right);
+    int node = pos, qq = 0, depth = 0, my_parent = -1;
+#pragma unroll
+    for (int dd = 1; dd <= 5; ++dd) {
+      const int lid = (1 << (dd - 1)) - 1 + qq;
+      if (depth != dd - 1 || !((vm >> lid) & 1u)) break;
+      if (lid == lane) my_parent = node;
+      const int r = (rm >> lid) & 1u;
+      node = (int)((((long long)pos + 1) << dd) - 1 + 2 * qq + r); qq = 2 * qq + r; depth = dd;
+    }
+    if (my_parent >= 0) OH_SET(my_parent, cf, ci);
+    __syncwarp();
+    pos = node;
+    if (depth < 5) break;
+  }
+  if (lane == 0) oh_siftdown<SMO>(sf, si, ge, nodes, pos, fi, item);
+  __syncwarp();
 }
 // in-place key update of an entry (hybrid_a_star.py:224-230: no re-heapify)
 template <int SMO>

@@ -73,6 +73,8 @@ __device__ __forceinline__ void ring_push(int *tail, int32_t *buf, int mask, int
 #ifndef AVP_CELL_SMEM
 #define AVP_CELL_SMEM (48 * 1024)
 #endif
+#define AVP_CAND_SMEM ((int)sizeof(RsCandX) * AVP_NCHILD_MAX * RS_NINST)
+#define AVP_PLAN_DYN_SMEM(block) (12 * avp_sm_open(block) + AVP_CELL_SMEM + AVP_CAND_SMEM)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -162,7 +164,6 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
   double *s_of = reinterpret_cast<double *>(s_dyn);
   int32_t *s_oi = reinterpret_cast<int32_t *>(s_dyn + sizeof(double) * SMO);
   __shared__ unsigned long long s_heap[AVP_SM_HEAP];
-  __shared__ RsCand s_cand[AVP_NCHILD_MAX][RS_NINST];
   __shared__ unsigned long long s_valid[AVP_NCHILD_MAX];
   __shared__ RsQuery s_Q[AVP_NCHILD_MAX];
   __shared__ double s_sub[AVP_NCHILD_MAX][4][4];
@@ -181,10 +182,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
   __shared__ int s_work2, s_work3, s_rs_done, s_course_rdy, s_q_rdy, s_sub_rdy, s_ins_done, s_cstride;   // the evaluators' queue: tail counter, finished rs items, course / rs queries / sub-step poses published, table inserts of the running commit done, stride of the course point order
   __shared__ VehGeom s_vg[BLOCK / 32];           // per warp: the vehicle rectangle of the pose being checked (check_distance_warp_sm)
   __shared__ DijCtx s_D;
+  __shared__ int s_sift_n;                                      // do_pop: heap size before the pop whose sift the whole commit warp runs (0: none)
   __shared__ __align__(8) unsigned long long s_cell_bar;       // mbarrier of the staged cell list
   unsigned char *s_cells = s_dyn + 12 * SMO;                   // AVP_CELL_SMEM bytes: double2 cells, then the int32 column starts
+  RsCandX (*s_cand)[RS_NINST] = reinterpret_cast<RsCandX (*)[RS_NINST]>(s_dyn + 12 * SMO + AVP_CELL_SMEM);   // AVP_CAND_SMEM bytes: word candidates of the successors, with their arranged lengths
   unsigned cell_parity = 0;
-  LPROF(__shared__ long long s_lp[8]; __shared__ long long s_lpe, s_lpc, s_lpt;)
+  LPROF(__shared__ long long s_lp[12]; __shared__ long long s_lpe, s_lpc, s_lpt;)
 #ifdef AVP_PROFILE
   __shared__ int s_trace_on;
   __shared__ long long s_ic[48];              // cycles per queue item (0..39: E1 items, 40/41: selections / course checks, 42/43: their counts)
@@ -297,8 +300,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
 #define SUBT(k) do { } while (0)
 #endif
 
-    // open_list.get() (path_planner.py:70) with the loop's exit tests; lane 0 of the commit warp
+    // open_list.get() (path_planner.py:70) with the loop's exit tests; lane 0 of the commit warp decides and leaves the size of the
+    // heap in s_sift_n, do_pop_warp then runs the heappop's sift (lane 0; the whole warp in the -DAVP_WARP_POP build)
     auto do_pop = [&]() {
+      s_sift_n = 0;
       if (dbg) { dbg[0] = 2; dbg[1] = s_npops; dbg[2] = s_D.closed_len; dbg[3] = s_on; }
       if (P.watchdog_cycles > 0 && clock64() - t_start > P.watchdog_cycles && s_status == 0) s_status = AVP_CAPACITY;
       if (s_status != 0 || s_on == 0) { s_ctlA = CTL_EXIT; return; }
@@ -319,8 +324,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         if (P.pop_fgh) { double *o = P.pop_fgh + ((size_t)sc * P.cap_pops + s_npops) * 3; o[0] = nodes[ret].f; o[1] = nodes[ret].g; o[2] = nodes[ret].h; }
       }
       s_npops++;
-      int n_ = s_on; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); s_on = n_;
+      s_sift_n = s_on; s_on = s_on - 1;
       s_ctlA = CTL_RUN;
+    };
+    auto do_pop_warp = [&](bool go) {           // called by every lane of warp 0
+      if (lane == 0 && go) do_pop();
+      __syncwarp();
+      const int n_before = s_sift_n;
+#ifdef AVP_WARP_POP
+      if (n_before > 0) oh_pop_fix_warp<SMO>(s_of, s_oi, oge, nodes, n_before, lane);
+#else
+      if (n_before > 0 && lane == 0) { int n_ = n_before; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); }
+#endif
+      __syncwarp();
     };
 
     // ---- take over the scenario: a fresh one starts at the root (the eager Dijkstra is done: k_dij_eager), a suspended one where
@@ -351,25 +367,26 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         r.in_radius = sqrt(d_pow2(r.x - goal[0]) + d_pow2(r.y - goal[1])) < cfg.flag_radius;
         nodes[0] = r;
         htab_insert(htab, hmask, nodes, 0);
-        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, oge, nodes, n_, 0.0, 0); s_on = n_; }
+        { int n_ = s_on; oh_push<SMO>(s_of, s_oi, oge, nodes, n_, 0.0, 0); s_on = n_; }      // an empty heap: position 0 is in shared memory
       } else if (warp == 1) {
         const double q0[3] = {S.pose[0], S.pose[1], pi_2_pi(S.pose[2])};
-        RsBest b; rs_length_warp(q0, goal, maxc, 1, 0, s_cand[0], b);
+        RsCand *rc = reinterpret_cast<RsCand *>(&s_cand[0][0]);          // scratch: nothing else uses s_cand before the first evaluation
+        RsBest b; rs_length_warp(q0, goal, maxc, 1, 0, rc, b);
         if (lane == 0) {
           NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
-          if (b.ok && !b.degenerate) { w.t = s_cand[0][b.inst].t; w.u = s_cand[0][b.inst].u; w.v = s_cand[0][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = 1; }
+          if (b.ok && !b.degenerate) { w.t = rc[b.inst].t; w.u = rc[b.inst].u; w.v = rc[b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = 1; }
           nshot[0] = w;
         }
       }
     }
     __syncthreads();
     if (staged) { mbar_wait(&s_cell_bar, cell_parity); cell_parity ^= 1u; }       // the cell list has landed
-    if (tid == 0) do_pop();                      // a fresh search: the first get() returns the root
+    if (warp == 0) { if (lane == 0) s_sift_n = 0; do_pop_warp(true); }     // a fresh search: the first get() returns the root
     PIPE_TICK(0, 0);
     PROF(if (tid == 32) tp = clock_ordered();)
 
     bool reached = false;
-    LPROF(if (tid < 8) s_lp[tid] = 0; if (tid == 32) s_lpe = clock_ordered(); if (tid == 0) s_lpc = clock_ordered();)
+    LPROF(if (tid < 12) s_lp[tid] = 0; if (tid == 32) s_lpe = clock_ordered(); if (tid == 0) s_lpc = clock_ordered();)
     for (;;) {
       __syncthreads();                                 // ---- barrier A: the evaluators' result is complete, the next node is popped
       LPROF(if (tid == 32) { const long long t_ = clock_ordered(); s_lp[0] += t_ - s_lpe; s_lpe = t_; } if (tid == 0) { s_lp[2] += clock_ordered() - s_lpc; s_lp[3] += 1; })
@@ -565,7 +582,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
                   const double f = s_g[i] + h;
                   n.h = h; n.f = f; n.in_open = 1;
                   PROF(const long long t_ = clock64();)
+                  LPROF(const long long tl_ = clock_ordered();)
                   oh_push<SMO>(s_of, s_oi, oge, nodes, on, f, child);
+                  LPROF(s_lp[8] += clock_ordered() - tl_; s_lp[9] += 1;)
                   PROF(pc[8] += clock64() - t_; pc[9]++;)
                 } else {                                                    // :219-230 (in place, no re-heapify)
                   const double new_f = h + s_g[i];
@@ -604,7 +623,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         TS(3);
         PIPE_TICK(0, 2);                         // node records + sequential commit
         LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[5] += t_ - s_lpt; s_lpt = t_; })
-        if (lane == 0 && (s_do_commit || s_status != 0)) do_pop();
+        if (lane == 0) s_sift_n = 0;
+        do_pop_warp(s_do_commit || s_status != 0);
         LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[7] += t_ - s_lpt; s_lpt = t_; })
         WP_ACC(2);
         TS(4);
@@ -778,9 +798,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
             if (inst >= 0) {
               double t, u, v;
               if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
-                RsCand c; c.t = t; c.u = u; c.v = v; c.L = 0.0;
-                c.L = rs_cand_L(inst, c, 1, 1);
-                s_cand[row][inst] = c; atomicOr(&s_valid[row], 1ull << inst);
+                RsCandX &c = s_cand[row][inst];                       // arranged once, here (rs_curve.py:200-534), and kept for the selection
+                double l[5], a[5]; int ct; unsigned mask;
+                const int n = rs_arrange(inst, t, u, v, 1, 1, l, ct, mask);
+                for (int q = 0; q < n; ++q) { a[q] = fabs(l[q]); c.len[q] = l[q]; }
+                c.t = t; c.u = u; c.v = v; c.n = n; c.ct = ct; c.mask = mask;
+                c.L = py_sum(a, n, mask);                              // rs_curve.py:148
+                atomicOr(&s_valid[row], 1ull << inst);
               }
             }
             __syncwarp();
@@ -863,15 +887,21 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
 #else
             const int half = lane >> 4, gl = lane & 15, i = 2 * it + half;
 #endif
-            if (i < nchild && gl < RS_NGROUP) rs_select_group(s_cand[i], s_valid[i], gl, 1, 1, maxc, s_grp[i][gl]);
+            if (i < nchild && gl < RS_NGROUP) rs_select_group_x(s_cand[i], s_valid[i], gl, maxc, s_grp[i][gl]);
             __syncwarp();
             if (i < nchild && gl == 0) {
-              RsBest b; rs_combine_groups(s_grp[i], s_cand[i], 1, 1, b);
-              const int ok = (b.ok && !b.degenerate) ? 1 : 0;
+              // calc_optimal_path over the group winners in order (rs_curve.py:99-110: the last word with L <= min wins)
+              int bi = -1, degenerate = 0; double minL = 0.0;
+              for (int g = 0; g < RS_NGROUP; ++g) {
+                degenerate |= s_grp[i][g].degenerate;
+                if (s_grp[i][g].inst < 0) continue;
+                if (bi < 0 || s_grp[i][g].Lm <= minL) { bi = s_grp[i][g].inst; minL = s_grp[i][g].Lm; }
+              }
+              const int ok = (bi >= 0 && !degenerate) ? 1 : 0;
               W.rsok[i] = ok;
-              W.rsL[i] = b.ok ? b.L / maxc : 0.0;
               NodeShot w; w.t = 0.0; w.u = 0.0; w.v = 0.0; w.L = 0.0; w.inst = -1; w.ok = 0;
-              if (b.ok) { w.t = s_cand[i][b.inst].t; w.u = s_cand[i][b.inst].u; w.v = s_cand[i][b.inst].v; w.L = b.L; w.inst = b.inst; w.ok = ok; }
+              if (bi >= 0) { const RsCandX &c = s_cand[i][bi]; W.rsL[i] = c.L / maxc; w.t = c.t; w.u = c.u; w.v = c.v; w.L = c.L; w.inst = bi; w.ok = ok; }
+              else W.rsL[i] = 0.0;
               W.shot[i] = w;
             }
           }
@@ -884,7 +914,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       }
     }
     __syncthreads();
-    LPROF(if (tid < 8 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
+    LPROF(if (tid < 12 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
 #ifdef AVP_PROFILE
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] += s_wp[warp][k]; }
     if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_ic[tid];

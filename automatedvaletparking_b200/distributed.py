@@ -83,3 +83,15 @@ def gather_results_device(dp, per_rank: int, cap_path: int, group=None):
     dist.all_gather_into_tensor(gs, ts, group=group)
     dist.all_gather_into_tensor(gp, tp, group=group)
     return gs, gp
+
+
+def records_checksum(summaries: np.ndarray, paths: np.ndarray) -> str:
+    """SHA-256 (first 16 hex digits) over the result records of a job in scenario order: the summaries and the rows of every
+    returned path.  Scenario sharding must not change it: bench.py prints it for every N (strong-scaling workloads)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(summaries).tobytes())
+    cap = paths.shape[1]
+    for k in range(len(summaries)):
+        h.update(np.ascontiguousarray(paths[k, :min(int(summaries["n_final"][k]), cap)]).tobytes())
+    return h.hexdigest()[:16]

@@ -26,7 +26,6 @@ primitive) slot of expand_node = sum of global_index (hybrid_a_star.py:239).
           of the same scenarios (rank 0, N=1 only).
 """
 import argparse
-import hashlib
 import json
 import os
 import statistics
@@ -146,15 +145,15 @@ def make_c4(dp=None, n_maps: int = 64, pairs: int = 64, n_poly: int = 256, colli
 
 
 def make_workload(name: str, rank: int, world: int, dp, n_c2: int = N_SCEN):
-    """-> (this rank's scenarios, total scenario count of the job, scaling, global ids of this rank's scenarios)"""
+    """-> (this rank's scenarios, total scenario count of the job, scaling, global ids of this rank's scenarios, shard keys)"""
     from automatedvaletparking_b200 import distributed as avd
     if name == "c2":
         scs = make_scenarios(rank, n_c2, dp)
-        return scs, n_c2 * world, "weak", np.arange(rank * n_c2, (rank + 1) * n_c2)
+        return scs, n_c2 * world, "weak", np.arange(rank * n_c2, (rank + 1) * n_c2), None
     full = make_c3(dp) if name == "c3" else make_c4(dp) if name == "c4" else make_c4(dp, n_poly=24, collision_free=True)
     keys = [avd.cost_proxy(s) for s in full]
     idx = avd.shard_indices(len(full), rank, world, keys)
-    return [full[i] for i in idx], len(full), "strong", idx
+    return [full[i] for i in idx], len(full), "strong", idx, keys
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -300,7 +299,7 @@ def run_workload(name, dp, rank, world, local_rank, W, K, n_c2, with_clocks, cpu
             dist.barrier()
         torch.cuda.synchronize()
 
-    scs, n_total, scaling, gids = make_workload(name, rank, world, dp, n_c2)
+    scs, n_total, scaling, gids, shard_keys = make_workload(name, rank, world, dp, n_c2)
     n = len(scs)
     batch = scn.pack(scs)
     dp.load(batch)                       # inputs resident: poses + polygons in HBM
@@ -362,14 +361,8 @@ def run_workload(name, dp, rank, world, local_rank, W, K, n_c2, with_clocks, cpu
         S = gs.cpu().numpy().view(s.dtype).reshape(world, per_rank)
         Pth = gp.cpu().numpy().reshape(world, per_rank, CAP_PATH, 3)
         if scaling == "strong":
-            allg = [None] * world
-            dist.all_gather_object(allg, np.asarray(gids))
-            sums_all = np.zeros(n_total, dtype=s.dtype)
-            paths_all = np.zeros((n_total, CAP_PATH, 3))
-            for r in range(world):
-                ids = allg[r]
-                sums_all[ids] = S[r][:len(ids)]
-                paths_all[ids] = Pth[r][:len(ids)]
+            sums_all = avd.unshard([S[r] for r in range(world)], n_total, world, shard_keys)
+            paths_all = avd.unshard([Pth[r] for r in range(world)], n_total, world, shard_keys)
         else:
             sums_all = S.reshape(-1)[:n_total]
             paths_all = Pth.reshape(-1, CAP_PATH, 3)[:n_total]
@@ -378,11 +371,7 @@ def run_workload(name, dp, rank, world, local_rank, W, K, n_c2, with_clocks, cpu
         paths_all = np.zeros((n_total, CAP_PATH, 3))
         sums_all[gids] = r2.summaries
         paths_all[gids] = r2.paths
-    h = hashlib.sha256()
-    h.update(np.ascontiguousarray(sums_all).tobytes())
-    for k in range(n_total):
-        h.update(np.ascontiguousarray(paths_all[k, :min(int(sums_all["n_final"][k]), CAP_PATH)]).tobytes())
-    checksum = h.hexdigest()[:16]
+    checksum = avd.records_checksum(sums_all, paths_all)
 
     # ---------------- reduce over ranks (max time, sum of units)
     t_search = statistics.mean(search_ms)

@@ -44,7 +44,7 @@ def _worker(rank, world, port, n, q):
     S, P = avd.gather_results(s, p, per_rank)
     full_s = avd.unshard([S[r] for r in range(world)], n, world, keys)
     full_p = avd.unshard([P[r] for r in range(world)], n, world, keys)
-    q.put((rank, mine.tolist(), full_s["global_index"].tolist(), full_p[:, 0, 0].tolist()))
+    q.put((rank, mine.tolist(), full_s["global_index"].tolist(), full_p[:, 0, 0].tolist(), avd.records_checksum(full_s, full_p)))
     dist.destroy_process_group()
 
 
@@ -63,9 +63,11 @@ def test_shard_and_gather_two_ranks(n):
     out.sort()
     ids0, ids1 = out[0][1], out[1][1]
     assert sorted(ids0 + ids1) == list(range(n)) and not set(ids0) & set(ids1)          # a partition
-    for _, _, gi, px in out:                                                          # every rank holds every record, in scenario order
+    s1, p1 = _stub_results(np.arange(n))                                              # what ONE rank produces for the whole job
+    for _, _, gi, px, cks in out:                                                     # every rank holds every record, in scenario order
         assert gi == [100 * i for i in range(n)]
         assert px == [i + 0.25 for i in range(n)]
+        assert cks == avd.records_checksum(s1, p1)                                    # sharding does not change the job's records
 
 
 def test_shard_count_invariance():

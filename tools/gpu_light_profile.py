@@ -12,7 +12,7 @@ from automatedvaletparking_b200.batch import DevicePlanner
 os.environ.setdefault("AVP_HOST_TIMEOUT_S", "300")
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 dp = DevicePlanner(max_pops=20000)
-scs, n_total, scaling, gids = bench.make_workload(name, 0, 1, dp)
+scs, n_total, scaling, gids, _ = bench.make_workload(name, 0, 1, dp)
 dp.load(scs)
 ms = dp.plan_resident(256, 0); ms = dp.plan_resident(256, 0)
 res = dp.fetch(256, 0)
@@ -28,6 +28,7 @@ for nm, idx in (("long (20000 pops)", np.where(s["n_pops"] >= 20000)[0]), ("mid 
           " | commit warp: records+inserts %6.0f  commit loop %6.0f  Dijkstra %6.0f  heappop %6.0f" %
           (nm, len(idx), s["n_pops"][idx].mean(), (pr[idx, 0] / pops).mean(), (pr[idx, 1] / pops).mean(), (pr[idx, 2] / pops).mean(),
            (pr[idx, 4] / pops).mean(), (pr[idx, 5] / pops).mean(), (pr[idx, 6] / pops).mean(), (pr[idx, 7] / pops).mean()))
+    print("%-18s pushes per pop %.2f, cycles per push %.0f (inside the commit loop)" % ("", (pr[idx, 9] / pops).mean(), pr[idx, 8].sum() / max(pr[idx, 9].sum(), 1.0)))
     tot = float(s["n_pops"][idx].sum())
     print("%-18s total pops %.0f" % ("", tot))
 dp.close()

@@ -18,7 +18,7 @@ os.environ.setdefault("AVP_HOST_TIMEOUT_S", "300")
 name = sys.argv[1]
 configs = sys.argv[2:] or [""]
 dp = DevicePlanner(max_pops=20000)
-scs, n_total, scaling, gids = bench.make_workload(name, int(os.environ.get("SWEEP_RANK", "0")), 1, dp)
+scs, n_total, scaling, gids, _ = bench.make_workload(name, int(os.environ.get("SWEEP_RANK", "0")), 1, dp)
 dp.load(scs)
 base = None
 touched = set()
