@@ -22,7 +22,7 @@ EXPORTS = [
     "avp_create", "avp_destroy", "avp_last_error", "avp_launch_count", "avp_scenarios_upload", "avp_rasterise",
     "avp_fetch_map", "avp_collision_check", "avp_check_start_goal", "avp_corridor", "avp_expand_pure", "avp_rs_optimal", "avp_plan_batch",
     "avp_plan_batch_resident", "avp_fetch_results", "avp_plan_configure", "avp_result_device_buffer",
-    "avp_split_paths", "avp_split_path", "avp_trace_fgh", "avp_fetch_pop_fgh", "avp_fetch_hvalues", "avp_fetch_hq_log", "avp_device_info", "avp_set_watchdog", "avp_fetch_debug", "avp_timer_start", "avp_timer_stop", "avp_last_search_ms", "avp_last_search_passes", "avp_fetch_profile", "avp_fetch_warp_profile", "avp_dijkstra_query",
+    "avp_split_paths", "avp_split_path", "avp_trace_fgh", "avp_fetch_pop_fgh", "avp_fetch_hvalues", "avp_fetch_hq_log", "avp_device_info", "avp_set_watchdog", "avp_fetch_debug", "avp_timer_start", "avp_timer_stop", "avp_last_search_ms", "avp_last_search_passes", "avp_last_narrow_ms", "avp_fetch_profile", "avp_fetch_warp_profile", "avp_dijkstra_query",
 ]
 
 _lib = None
@@ -79,6 +79,7 @@ def lib():
     L.avp_fetch_warp_profile.argtypes = [c_vp, c_lp]
     L.avp_dijkstra_query.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_ip, c_ip, c_ip]
     L.avp_last_search_passes.argtypes = [c_vp, c_fp, c_fp, c_ip]
+    L.avp_last_narrow_ms.argtypes = [c_vp, c_fp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = the header and the library disagree
     _lib = L

@@ -283,6 +283,12 @@ class DevicePlanner:
         self._ck(self._L.avp_last_search_passes(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)), "avp_last_search_passes")
         return float(a.value), float(b.value), int(n.value) % 100000, int(n.value) // 100000
 
+    def last_narrow_ms(self) -> float:
+        """CUDA-event time of the narrow first search launch of the last plan (0: one launch did everything)"""
+        ms = ctypes.c_float()
+        self._ck(self._L.avp_last_narrow_ms(self._h, ctypes.byref(ms)), "avp_last_narrow_ms")
+        return float(ms.value)
+
     def dijkstra_query(self, s: int, x: float, y: float, reset: bool = False):
         """Dijkstra.compute_path(x, y) of scenario s -> (distance, len(closedlist), terminate_grid_id)"""
         d, c, t = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()

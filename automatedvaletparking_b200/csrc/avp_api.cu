@@ -41,7 +41,7 @@ struct avp_ctx {
   ScenState *d_state = nullptr; PlanCtl *d_ctl = nullptr; int32_t *d_queue = nullptr, *d_slot_ring = nullptr; int q_mask = 0, slot_mask = 0;
   int32_t *d_order = nullptr;      // processing order: expensive scenarios (far start-goal pairs) first
   double *d_course = nullptr; int32_t *d_course_dir = nullptr;
-  int plan_block = 512, plan_grid = 0, ctas_per_sm[2] = {1, 2};
+  int plan_block = 512, plan_grid = 0, ctas_per_sm[2] = {1, 2}, narrow_per_sm = 1; float narrow_ms = 0.f; cudaEvent_t evN = nullptr;
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
   int cap_path = 0, cap_pops = 0; int res_n = 0;
@@ -94,16 +94,18 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return -8; }
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -9; }
-  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(512));
-  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(256));
-  cudaFuncSetAttribute(k_plan<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(640));
+  cudaFuncSetAttribute(k_plan<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(512, AVP_CELL_SMEM));
+  cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(256, AVP_CELL_SMEM));
+  cudaFuncSetAttribute(k_plan<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(640, AVP_CELL_SMEM));
+  cudaFuncSetAttribute(k_plan<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(128, 0));
   {
     int o = 0;
-    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, AVP_PLAN_DYN_SMEM(512)) == cudaSuccess && o > 0) ? o : 1;
-    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, AVP_PLAN_DYN_SMEM(256)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, AVP_PLAN_DYN_SMEM(512, AVP_CELL_SMEM)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, AVP_PLAN_DYN_SMEM(256, AVP_CELL_SMEM)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->narrow_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<128>, 128, AVP_PLAN_DYN_SMEM(128, 0)) == cudaSuccess && o > 0) ? o : 1;
   }
   ctx->slots = ctx->n_sm * ctx->ctas_per_sm[0];               // persistent grids: multiples of the SM count
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evM);
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evM); cudaEventCreate(&ctx->evN);
   if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return -10; }
   *out = ctx;
   return 0;
@@ -136,7 +138,7 @@ extern "C" int avp_destroy(avp_ctx *ctx) {
   free_dev(ctx->d_counter); free_dev(ctx->d_scratch); free_dev(ctx->d_cell_total); free_dev(ctx->d_pop_fgh);
   free_dev(ctx->d_order);
   free_dev(ctx->d_dq_gheap); free_dev(ctx->d_dq_state); free_dev(ctx->d_dq_out);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1); if (ctx->evM) cudaEventDestroy(ctx->evM);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1); if (ctx->evM) cudaEventDestroy(ctx->evM); if (ctx->evN) cudaEventDestroy(ctx->evN);
   if (ctx->evA) cudaEventDestroy(ctx->evA); if (ctx->evB) cudaEventDestroy(ctx->evB);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -458,7 +460,18 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   { const char *be = getenv("AVP_PLAN_BLOCK"); if (be && (atoi(be) == 256 || atoi(be) == 640)) block = atoi(be); }
   const int per_sm = block == 256 ? ctx->ctas_per_sm[1] : 1;
   int grid = ctx->n_sm * per_sm; if (grid > ctx->n) grid = ctx->n;
-  if (ensure_ws(ctx, ctx->n_sm * ctx->ctas_per_sm[1] > grid ? ctx->n_sm * ctx->ctas_per_sm[1] : grid)) return -1;
+  // Two launches for batches with more scenarios than a wave of wide CTAs: most searches are short (C2: median 19 pops) and their time
+  // is the single-warp Dijkstra resumes, during which a 512-thread CTA idles.  A first launch of NARROW CTAs (128 threads, three per
+  // SM) gives every fresh scenario a few pops -- the short ones finish there, twelve Dijkstra warps per SM instead of one --, every
+  // unfinished search goes to the run queue, and the wide launch resumes them (stream order: no host round trip, nothing re-planned).
+  bool two_phase = ctx->n > 2 * ctx->n_sm;
+  { const char *te = getenv("AVP_TWO_PHASE"); if (te) two_phase = atoi(te) != 0; }
+  int grid_n = ctx->n_sm * ctx->narrow_per_sm; if (grid_n > ctx->n) grid_n = ctx->n;
+  {
+    int need = ctx->n_sm * ctx->ctas_per_sm[1] > grid ? ctx->n_sm * ctx->ctas_per_sm[1] : grid;
+    if (grid_n > need) need = grid_n;
+    if (ensure_ws(ctx, need)) return -1;
+  }
   PlanParams PP; memset(&PP, 0, sizeof(PP));
   KParams &P = PP.K;
   P.cfg = ctx->cfg; if (P.cfg.max_pops <= 0) P.cfg.max_pops = 20000;
@@ -480,6 +493,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   { const char *qe = getenv("AVP_QUANTUM"); PP.quantum = (qe && atoi(qe) > 0) ? atoi(qe) : 512; }
   { const char *oe = getenv("AVP_OVERFLOW_ODD"); PP.overflow_odd = (oe && atoi(oe) == 0) ? 0 : 1; }
   { const char *fe = getenv("AVP_FORCE_YIELD"); PP.force_yield = (fe && atoi(fe) != 0) ? 1 : 0; }
+  PP.phase = two_phase ? 1 : 0; PP.cell_smem = AVP_CELL_SMEM;
   // SM pairs: only when the grid covers every SM (else the hardware's placement decides) and not switched off (AVP_SPREAD=0)
   { const char *se = getenv("AVP_SPREAD"); P.spread = (grid == ctx->n_sm * per_sm && ctx->n_sm >= 4 && !(se && atoi(se) == 0)) ? 1 : 0; }
   { const char *me = getenv("AVP_SPREAD_MAX"); PP.spread_max = me ? atoi(me) : (ctx->n_sm / 2 + ctx->n_sm / 4) * per_sm; }
@@ -495,9 +509,17 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
     k_dij_eager<<<dgrid, AVP_DIJ_WARPS * 32, 0, ctx->stream>>>(PP); ctx->launches++;
   }
   CK(cudaEventRecord(ctx->evM, ctx->stream));
-  if (block == 512) k_plan<512><<<grid, 512, AVP_PLAN_DYN_SMEM(512), ctx->stream>>>(PP);
-  else if (block == 640) k_plan<640><<<grid, 640, AVP_PLAN_DYN_SMEM(640), ctx->stream>>>(PP);
-  else k_plan<256><<<grid, 256, AVP_PLAN_DYN_SMEM(256), ctx->stream>>>(PP);
+  if (two_phase) {
+    PlanParams P1 = PP;
+    P1.phase = 1; P1.cell_smem = 0; P1.K.spread = 0;
+    { const char *be = getenv("AVP_NARROW_BUDGET"); P1.quantum = (be && atoi(be) > 0) ? atoi(be) : 128; }
+    k_plan<128><<<grid_n, 128, AVP_PLAN_DYN_SMEM(128, 0), ctx->stream>>>(P1); ctx->launches++;
+    PP.phase = 2;
+  }
+  CK(cudaEventRecord(ctx->evN, ctx->stream));
+  if (block == 512) k_plan<512><<<grid, 512, AVP_PLAN_DYN_SMEM(512, AVP_CELL_SMEM), ctx->stream>>>(PP);
+  else if (block == 640) k_plan<640><<<grid, 640, AVP_PLAN_DYN_SMEM(640, AVP_CELL_SMEM), ctx->stream>>>(PP);
+  else k_plan<256><<<grid, 256, AVP_PLAN_DYN_SMEM(256, AVP_CELL_SMEM), ctx->stream>>>(PP);
   ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaGetLastError());
@@ -506,6 +528,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   float ms1 = 0.f, ms2 = 0.f;
   CK(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->evM));
   CK(cudaEventElapsedTime(&ms2, ctx->evM, ctx->ev1));
+  { float msn = 0.f; CK(cudaEventElapsedTime(&msn, ctx->evM, ctx->evN)); ctx->narrow_ms = two_phase ? msn : 0.f; }
   ctx->pass_ms[0] = ms1; ctx->pass_ms[1] = ms2;
   if (elapsed_ms) *elapsed_ms = ms1 + ms2;
   PlanCtl c;
@@ -684,6 +707,9 @@ extern "C" int avp_last_search_passes(avp_ctx *ctx, float *ms_dijkstra, float *m
   if (n_info) *n_info = (ctx->n_suspends % 100000) + 100000 * ctx->plan_block;
   return 0;
 }
+
+/* CUDA-event time of the narrow first search launch of the last plan (0: the batch was planned by one launch) */
+extern "C" int avp_last_narrow_ms(avp_ctx *ctx, float *ms) { if (!ctx) return -3; if (ms) *ms = ctx->narrow_ms; return 0; }
 
 /* per-scenario SM-cycle accumulators of the search kernel's phases (thread 0 of the CTA):
  * [0] init + eager Dijkstra, [1] loop top, [2] heappop + poses/queries, [3] lookups + collision checks +

@@ -44,6 +44,14 @@ struct ScenDev {
 // one copy of each body per kernel keeps code size and register pressure down.
 __device__ __noinline__ double d_sin(double x) { return avp_sin(x); }
 __device__ __noinline__ double d_cos(double x) { return avp_cos(x); }
+// sine AND cosine of one argument in one function: the same two restatements, inlined side by side so that the compiler interleaves
+// their (independent) dependency chains -- the bits are those of d_sin / d_cos, the latency is that of one of them plus a little
+// (the evaluation is bound by fixed-latency fp64 dependencies, profiles/ncu_kplan_r02.csv: "wait" is its largest stall)
+#ifdef AVP_NO_SINCOS     // A/B build: two calls
+__device__ __forceinline__ void d_sincos(double x, double &s, double &c) { s = d_sin(x); c = d_cos(x); }
+#else
+__device__ __noinline__ void d_sincos(double x, double &s, double &c) { s = avp_sin(x); c = avp_cos(x); }
+#endif
 __device__ __noinline__ double d_atan2(double y, double x) { return avp_atan2(y, x); }
 __device__ __noinline__ double d_asin(double x) { return avp_asin(x); }
 __device__ __noinline__ double d_acos(double x) { return avp_acos(x); }
@@ -383,7 +391,8 @@ __device__ __forceinline__ bool check_pose_cs_warp_sm(const avp_config &c, const
 }
 __device__ __forceinline__ bool check_pose_warp(const avp_config &c, const ScenDev &S, const double2 *cells,
                                                 const int32_t *col_start, double x, double y, double th) {
-  return check_pose_cs_warp(c, S, cells, col_start, x, y, d_cos(th), d_sin(th));
+  double sn, cs; d_sincos(th, sn, cs);
+  return check_pose_cs_warp(c, S, cells, col_start, x, y, cs, sn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -453,9 +462,11 @@ __device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double sp
 }
 // rs_curve.py:308-323
 __device__ __forceinline__ void rs_tauOmega(double u, double v, double xi, double eta, double phi, double &tau, double &omega) {
-  const double delta = rs_M(u - v), A = d_sin(u) - d_sin(delta), B = d_cos(u) - d_cos(delta) - 1.0;
+  const double delta = rs_M(u - v);
+  double su, cu, sd, cd; d_sincos(u, su, cu); d_sincos(delta, sd, cd);
+  const double A = su - sd, B = cu - cd - 1.0;
   const double t1 = d_atan2(eta * A - xi * B, xi * A + eta * B);
-  const double t2 = 2.0 * (d_cos(delta) - d_cos(v) - d_cos(u)) + 3.0;
+  const double t2 = 2.0 * (cd - d_cos(v) - cu) + 3.0;
   tau = (t2 < 0) ? rs_M(t1 + AVP_PI) : rs_M(t1);
   omega = rs_M(tau - u + v - phi);
 }
@@ -523,12 +534,13 @@ struct RsQuery { double x, y, phi, xb, yb, sp, cp; };   // sp, cp = sin(phi), co
 __device__ __forceinline__ void rs_query_cs(const double q0[3], double c, double s, const double q1[3], double maxc, RsQuery &Q) {
   const double dx = q1[0] - q0[0], dy = q1[1] - q0[1], dth = q1[2] - q0[2];
   Q.x = (c * dx + s * dy) * maxc; Q.y = (-s * dx + c * dy) * maxc; Q.phi = dth;
-  const double cp = d_cos(dth), sp = d_sin(dth);
+  double cp, sp; d_sincos(dth, sp, cp);
   Q.sp = sp; Q.cp = cp;
   Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;          // rs_curve.py:286-287, :456-457
 }
 __device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
-  rs_query_cs(q0, d_cos(q0[2]), d_sin(q0[2]), q1, maxc, Q);
+  double s0, c0; d_sincos(q0[2], s0, c0);
+  rs_query_cs(q0, c0, s0, q1, maxc, Q);
 }
 
 // one word instance -> (valid, t, u, v)
@@ -680,12 +692,14 @@ __device__ __forceinline__ void rs_select(RsCand *cand, unsigned long long valid
 __device__ __noinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
                                                double &px, double &py, double &pyaw, int &dir) {
   if (m == 'S') {
-    px = ox + l / maxc * d_cos(oyaw); py = oy + l / maxc * d_sin(oyaw); pyaw = oyaw;
+    double so, co; d_sincos(oyaw, so, co);
+    px = ox + l / maxc * co; py = oy + l / maxc * so; pyaw = oyaw;
   } else {
-    const double ldx = d_sin(l) / maxc;
+    double sl, cl; d_sincos(l, sl, cl);
+    const double ldx = sl / maxc;
     double ldy = 0.0;
-    if (m == 'L') ldy = (1.0 - d_cos(l)) / maxc; else if (m == 'R') ldy = (1.0 - d_cos(l)) / (-maxc);
-    const double cm = d_cos(-oyaw), sm = d_sin(-oyaw);
+    if (m == 'L') ldy = (1.0 - cl) / maxc; else if (m == 'R') ldy = (1.0 - cl) / (-maxc);
+    double cm, sm; d_sincos(-oyaw, sm, cm);
     const double gdx = cm * ldx + sm * ldy, gdy = -sm * ldx + cm * ldy;
     px = ox + gdx; py = oy + gdy;
   }

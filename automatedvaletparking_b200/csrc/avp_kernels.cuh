@@ -606,23 +606,10 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
     // the popped cell is expanded next: its neighbours' state words and cost-map bytes are prefetched while lane 0 sifts (the
     // positions are estimated from the id -- ids and raster indices are floors of the same lattice coordinates; a wrong guess
     // only costs the prefetch)
-    // ... and one pop further ahead: the root after this pop is (almost always) one of the root's two children, so their lattice
-    // coordinates and their neighbourhoods are prefetched as well (lanes 8..21)
-    {
-      int pid = -1, role = 0;
-      if (lane >= 1 && lane <= 6) { pid = cur_id; role = lane; }
-#ifndef AVP_NO_DIJ_AHEAD     // A/B build
-      else if (lane >= 8 && lane <= 14 && hn > 1) { pid = (int)(unsigned)sheap[1]; role = lane - 8; }
-      else if (lane >= 15 && lane <= 21 && hn > 2) { pid = (int)(unsigned)sheap[2]; role = lane - 15; }
-#endif
-      if (pid >= 0 && pid < n_ids) {
-        if (role == 0) { prefetch_l1(&gxa[pid]); prefetch_l1(&gya[pid]); }
-        else {
-          const int i1 = pid / stride, i0 = pid - i1 * stride;
-          if (role <= 3) { const int q = (i1 + role - 2) * stride + i0 - 1; if (q >= 0 && q + 2 < n_ids) { prefetch_l1(&ost[q]); prefetch_l1(&ost[q + 2]); } }
-          else { const int xi = i0 - 1 + (role - 5), yi = my - i1 - 3; if (xi >= 0 && xi < nx && yi >= 0 && yi + 2 < ny) { prefetch_l1(&cost[(size_t)xi * ny + yi]); prefetch_l1(&cost[(size_t)xi * ny + yi + 2]); } }
-        }
-      }
+    if (lane >= 1 && lane <= 6) {      // (prefetching one pop further ahead -- the root's two children -- measured 1.5 % slower: not done)
+      const int i1 = cur_id / stride, i0 = cur_id - i1 * stride;
+      if (lane <= 3) { const int q = (i1 + lane - 2) * stride + i0 - 1; if (q >= 0 && q + 2 < n_ids) { prefetch_l1(&ost[q]); prefetch_l1(&ost[q + 2]); } }
+      else { const int xi = i0 - 1 + (lane - 5), yi = my - i1 - 3; if (xi >= 0 && xi < nx && yi >= 0 && yi + 2 < ny) { prefetch_l1(&cost[(size_t)xi * ny + yi]); prefetch_l1(&cost[(size_t)xi * ny + yi + 2]); } }
     }
 #ifdef AVP_DIJ_SERIAL_POP       // A/B build: the serial sift of round 1
     if (lane == 0) {

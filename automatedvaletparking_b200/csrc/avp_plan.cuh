@@ -31,7 +31,7 @@ struct __align__(16) ScenState {
   int32_t nhq, nhcalls, G, nclosed, npops, on, cur, in_radius, best_ok;
   int32_t quanta, pad;
 };
-struct PlanCtl { int q_head, q_tail, finalised, slot_head, slot_tail, n_suspends, n_requeues, error; };
+struct PlanCtl { int q_head, q_tail, finalised, slot_head, slot_tail, n_suspends, n_requeues, error, fresh_next, pad[3]; };
 
 struct PlanParams {
   KParams K;                     // cfg, scenario arrays, results (work_list = initial order of the run queue)
@@ -41,6 +41,9 @@ struct PlanParams {
   int32_t *slot_ring; int slot_mask; int n_slots;
   int quantum;                   // pops per turn while others wait
   int spread_max;                // the CTAs on odd SM ids only work while more scenarios than this are live (P.K.spread)
+  int phase;                     // 0: one launch does everything; 1: the narrow first launch (fresh scenarios from work_list, a few pops each, then
+                                 //    every unfinished search is left in the run queue); 2: the wide second launch (the run queue)
+  int cell_smem;                 // bytes of the TMA staging window in dynamic shared memory (0: the cell list stays in global memory)
   int overflow_odd;              // the CTAs on odd SM ids take searches that WAIT in the queue even while they stand back (AVP_OVERFLOW_ODD=0: off)
   int force_yield;               // development aid: let go of the scenario at EVERY quantum end (tests of the suspend / resume path on small batches)
 };
@@ -74,7 +77,7 @@ __device__ __forceinline__ void ring_push(int *tail, int32_t *buf, int mask, int
 #define AVP_CELL_SMEM (48 * 1024)
 #endif
 #define AVP_CAND_SMEM ((int)sizeof(RsCandX) * AVP_NCHILD_MAX * RS_NINST)
-#define AVP_PLAN_DYN_SMEM(block) (12 * avp_sm_open(block) + AVP_CELL_SMEM + AVP_CAND_SMEM)
+#define AVP_PLAN_DYN_SMEM(block, cell_smem) (12 * avp_sm_open(block) + AVP_CAND_SMEM + (cell_smem))
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -93,9 +96,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 
 __global__ void k_plan_init(PlanParams P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= P.q_mask) P.queue[i] = (i < P.K.n_work) ? (P.K.work_list ? P.K.work_list[i] : i) : -1;
+  if (i <= P.q_mask) P.queue[i] = (P.phase == 0 && i < P.K.n_work) ? (P.K.work_list ? P.K.work_list[i] : i) : -1;
   if (i <= P.slot_mask) P.slot_ring[i] = (i < P.n_slots) ? i : -1;
-  if (i == 0) { PlanCtl c; c.q_head = 0; c.q_tail = P.K.n_work; c.finalised = 0; c.slot_head = 0; c.slot_tail = P.n_slots; c.n_suspends = 0; c.n_requeues = 0; c.error = 0; *P.ctl = c; *P.K.work_counter = 0; }
+  if (i == 0) { PlanCtl c; c.q_head = 0; c.q_tail = (P.phase == 0) ? P.K.n_work : 0; c.fresh_next = 0; c.pad[0] = c.pad[1] = c.pad[2] = 0; c.finalised = 0; c.slot_head = 0; c.slot_tail = P.n_slots; c.n_suspends = 0; c.n_requeues = 0; c.error = 0; *P.ctl = c; *P.K.work_counter = 0; }
 }
 
 #define AVP_DIJ_WARPS 4
@@ -184,8 +187,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
   __shared__ DijCtx s_D;
   __shared__ int s_sift_n;                                      // do_pop: heap size before the pop whose sift the whole commit warp runs (0: none)
   __shared__ __align__(8) unsigned long long s_cell_bar;       // mbarrier of the staged cell list
-  unsigned char *s_cells = s_dyn + 12 * SMO;                   // AVP_CELL_SMEM bytes: double2 cells, then the int32 column starts
-  RsCandX (*s_cand)[RS_NINST] = reinterpret_cast<RsCandX (*)[RS_NINST]>(s_dyn + 12 * SMO + AVP_CELL_SMEM);   // AVP_CAND_SMEM bytes: word candidates of the successors, with their arranged lengths
+  RsCandX (*s_cand)[RS_NINST] = reinterpret_cast<RsCandX (*)[RS_NINST]>(s_dyn + 12 * SMO);   // AVP_CAND_SMEM bytes: word candidates of the successors, with their arranged lengths
+  unsigned char *s_cells = s_dyn + 12 * SMO + AVP_CAND_SMEM;   // PP.cell_smem bytes: double2 cells, then the int32 column starts
   unsigned cell_parity = 0;
   LPROF(__shared__ long long s_lp[12]; __shared__ long long s_lpe, s_lpc, s_lpt;)
 #ifdef AVP_PROFILE
@@ -214,6 +217,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
     if (tid == 0) {
       int got = -1;
       long long t_last = clock64(); int last = -1; const long long t_idle = t_last; bool seen_waiting = false; long long t_wait = 0;
+      if (PP.phase == 1) {                       // the narrow first launch: the next fresh scenario of the work list, or done
+        const int k = atomicAdd(&ctl->fresh_next, 1);
+        if (k < P.n_work) got = P.work_list ? P.work_list[k] : k;
+      } else
       for (;;) {
         const int fin = *(volatile int *)&ctl->finalised;
         if (fin >= P.n_work) break;
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         if (phase == 0 && st.z == 0) {
           slot = ring_pop(&ctl->slot_head, &ctl->slot_tail, PP.slot_ring, PP.slot_mask);
           if (slot < 0) {       // every slot is held by a suspended search: this one goes to the back of the queue, a suspended one will come up
-            ring_push(&ctl->q_tail, PP.queue, PP.q_mask, got); atomicAdd(&ctl->n_requeues, 1); got = -2; __nanosleep(2000);
+            ring_push(&ctl->q_tail, PP.queue, PP.q_mask, got); atomicAdd(&ctl->n_requeues, 1); got = -2; if (PP.phase != 1) __nanosleep(2000);
           }
         }
       }
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
     const unsigned cell_bytes = (unsigned)S.n_obs * (unsigned)sizeof(double2), col_bytes = (((unsigned)S.nx + 1u) * 4u + 15u) & ~15u;
-    const bool staged = slot >= 0 && S.n_obs > 0 && cell_bytes + col_bytes <= AVP_CELL_SMEM;
+    const bool staged = slot >= 0 && S.n_obs > 0 && (int)(cell_bytes + col_bytes) <= PP.cell_smem;
     if (staged) {
       if (tid == 0) {
         mbar_expect_tx(&s_cell_bar, cell_bytes + col_bytes);
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
     int32_t *hql = P.hq_log ? P.hq_log + (size_t)sc * AVP_HQ_CAP * 3 : nullptr;
     int *dbg = P.dbg ? P.dbg + (size_t)sc * 8 : nullptr;
     const long long t_start = clock64();
+    LPROF(unsigned long long gt_take = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_take));)
 #ifdef AVP_PROFILE
     // cycle accumulators: thread 0 (commit warp) and thread 32 (evaluators) each keep their own
     long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = t_start;
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         const int fin = *(volatile int *)&ctl->finalised;
         const bool waiting = (*(volatile int *)&ctl->q_head - *(volatile int *)&ctl->q_tail) < 0;
         const bool stand_back = P.spread && s_odd && (P.n_work - fin <= PP.spread_max);
-        if (waiting || stand_back || PP.force_yield) { s_status = AVP_PENDING; s_ctlA = CTL_EXIT; return; }
+        if (waiting || stand_back || PP.force_yield || PP.phase == 1) { s_status = AVP_PENDING; s_ctlA = CTL_EXIT; return; }
         s_limit = s_npops + PP.quantum;
       }
       const int ret = s_oi[0];
@@ -558,6 +566,52 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
           int i = 0, n_miss = 0;
           int on = s_on;
           oh_prefetch_push<SMO>(oge, on, nchild, lane);            // the ancestors of the positions this commit pushes to
+#ifndef AVP_SERIAL_COMMIT
+          // FAST PATH (no successor misses its h value: all but ~0.3 % of the commits): what is independent per successor -- h, f,
+          // the node fields, the counters -- is done by lanes 0..nchild-1 at once; only the heap operations, whose order is the
+          // heap's structure, run one after the other (lane 0, slot order).  Same values, same order of heap operations.
+          const unsigned miss_m = __ballot_sync(AVP_FULL_MASK, lane < nchild && s_need[lane] && s_hv[lane] < 0);
+          if (miss_m == 0u) {
+            int act = 0; double fv = 0.0;                        // 1 closed on creation, 2 push, 3 in-place update
+            if (lane < nchild && !s_skip[lane]) {
+              const int found = s_found[lane];
+              if (found < 0 && R.coll[lane]) act = 1;
+              else {
+                const double h1 = s_h1[lane], h2 = R.rsL[lane];
+                const double h = (h2 > h1) ? h2 : h1;                       // max(h_value_1, h_value_2) (:294-296)
+                if (found < 0) {                                            // :206-216
+                  Node &n = nodes[s_G + lane + 1];
+                  fv = s_g[lane] + h;
+                  n.h = h; n.f = fv; n.in_open = 1;
+                  act = 2;
+                } else {                                                    // :219-230 (in place, no re-heapify)
+                  fv = h + s_g[lane];
+                  if (fv < s_oldf[lane]) {
+                    Node &n = nodes[found];
+                    n.f = fv; n.g = s_g[lane]; n.h = h; n.parent = cur; n.forward = (lane < nchild / 2.0) ? 1 : 0; n.steer_idx = (uint8_t)(lane % cfg.steering_angle_num);
+                    act = 3;
+                  } else act = 4;
+                }
+              }
+            }
+            const unsigned closed_m = __ballot_sync(AVP_FULL_MASK, act == 1), h_m = __ballot_sync(AVP_FULL_MASK, act >= 2);
+            const unsigned push_m = __ballot_sync(AVP_FULL_MASK, act == 2), upd_m = __ballot_sync(AVP_FULL_MASK, act == 3);
+            if (lane == 0) { s_nclosed += __popc(closed_m); s_nhcalls += __popc(h_m); }
+            unsigned todo = push_m | upd_m;
+            while (todo) {
+              const int k = __ffs(todo) - 1; todo &= todo - 1;
+              const double fk = shfl_d(fv, k);
+              if (lane == 0) {
+                if ((push_m >> k) & 1u) {
+                  LPROF(const long long tl_ = clock_ordered();)
+                  oh_push<SMO>(s_of, s_oi, oge, nodes, on, fk, s_G + k + 1);
+                  LPROF(s_lp[8] += clock_ordered() - tl_; s_lp[9] += 1;)
+                } else oh_set_key<SMO>(s_of, oge, nodes[s_found[k]].hpos, fk);
+              }
+            }
+            i = nchild;
+          }
+#endif
           for (;;) {
             int stop = nchild;
             if (lane == 0) {
@@ -676,7 +730,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
                   if ((int)(b.L / (0.5 * maxc)) + b.n + 3 > AVP_COURSE_CAP) s_shot_bad = 2;
                 }
                 s_best = b;
-                s_tcs[0] = d_cos(-T.theta); s_tcs[1] = d_sin(-T.theta);
+                { double st_, ct_; d_sincos(-T.theta, st_, ct_); s_tcs[0] = ct_; s_tcs[1] = st_; }
               }
               __syncwarp();
               if (!s_shot_bad) {
@@ -742,7 +796,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               const double speed = (c < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
               const double td = speed * cfg.dt;
               q0[2] = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
-              const double cs = d_cos(q0[2]), sn = d_sin(q0[2]);
+              double cs, sn; d_sincos(q0[2], sn, cs);
               q0[0] = T.x + td * cs; q0[1] = T.y + td * sn;
               W.cpose[c][0] = q0[0]; W.cpose[c][1] = q0[1]; W.cpose[c][2] = q0[2];
               rs_query_cs(q0, cs, sn, goal, maxc, s_Q[c]);
@@ -757,7 +811,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
               const double td_i = speed * cfg.ddt * (k + 1);
               const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-              const double cs = d_cos(th_i), sn = d_sin(th_i);
+              double cs, sn; d_sincos(th_i, sn, cs);
               s_sub[i][k][0] = T.x + td_i * cs; s_sub[i][k][1] = T.y + td_i * sn; s_sub[i][k][2] = cs; s_sub[i][k][3] = sn;
             }
             __syncwarp();
@@ -817,7 +871,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
             const int i = it - 4 - RS_NITEM;
 #endif
             int coll = 0;
-            for (int k = 0; k < nsubs; ++k) {
+            for (int kk = 0; kk < nsubs; ++kk) {
+              // any hit decides (hybrid_a_star.py:185-204 breaks at the first one): the sub-steps are checked farthest first -- the parent pose
+              // is collision free, so the sub-step next to it is the least likely to hit
+#ifdef AVP_SUB_FORWARD
+              const int k = kk;
+#else
+              const int k = nsubs - 1 - kk;
+#endif
               bool hit;
               if (k < 4) hit = check_pose_cs_warp_sm(cfg, S, cells, col_start, s_sub[i][k][0], s_sub[i][k][1], s_sub[i][k][2], s_sub[i][k][3], vg);
               else {
@@ -825,7 +886,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
                 const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
                 const double td_i = speed * cfg.ddt * (k + 1);
                 const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
-                const double cs = d_cos(th_i), sn = d_sin(th_i);
+                double cs, sn; d_sincos(th_i, sn, cs);
                 hit = check_pose_cs_warp_sm(cfg, S, cells, col_start, T.x + td_i * cs, T.y + td_i * sn, cs, sn, vg);
               }
               if (hit) { coll = 1; break; }
@@ -847,7 +908,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         if (warp == 0) { WP_ACC(3); LPROF(if (tid == 0) s_lpc = clock_ordered();) continue; }
         if (!wait_ge_cta(&s_course_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; continue; }
         const int npts = s_npts, cstride = s_cstride;
-#ifdef AVP_RS_FINE
+#if defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
         const int n_sel = nchild;
 #else
         const int n_sel = (nchild + 1) / 2;
@@ -880,9 +941,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
             const double gx_ = cm * ix + sm * iy + T.x, gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
             const double gyaw = pi_2_pi(CYAW[j] + T.theta);
             const double gth = pi_2_pi(gyaw);
-            if (check_pose_cs_warp_sm(cfg, S, cells, col_start, gx_, gy_, d_cos(gth), d_sin(gth), vg)) { if (lane == 0) s_shot_coll = 1; }
+            double gsn, gcs; d_sincos(gth, gsn, gcs);
+            if (check_pose_cs_warp_sm(cfg, S, cells, col_start, gx_, gy_, gcs, gsn, vg)) { if (lane == 0) s_shot_coll = 1; }
           } else {
-#ifdef AVP_RS_FINE
+#if defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
             const int gl = lane, i = (lane < 16) ? it : nchild;
 #else
             const int half = lane >> 4, gl = lane & 15, i = 2 * it + half;
@@ -914,7 +976,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       }
     }
     __syncthreads();
-    LPROF(if (tid < 12 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
+    LPROF(if (tid < 10 && P.prof) P.prof[(size_t)sc * 16 + tid] += s_lp[tid];)
+    LPROF(if (tid == 0 && P.prof) { long long *o = P.prof + (size_t)sc * 16; unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                                     o[10] += clock64() - t_start;                 // cycles this scenario held an SM
+                                     if (st0.quanta == 0 && fresh) o[11] = (long long)gt_take;        // wall clock (ns) of its first take-over
+                                     o[12] = (long long)gt;                        // ... of its latest release (the finish, in the end)
+                                     o[13] += 1; })
 #ifdef AVP_PROFILE
     if (lane == 0 && P.wprof && warp < 16) { long long *o = P.wprof + ((size_t)sc * 16 + warp) * 24; for (int k = 0; k < 8; ++k) o[k] += s_wp[warp][k]; }
     if (tid < 48 && P.wprof) P.wprof[((size_t)sc * 16 + (tid >> 3)) * 24 + 16 + (tid & 7)] += s_ic[tid];

@@ -218,6 +218,9 @@ int avp_last_search_ms(avp_ctx *ctx, float *elapsed_ms);
  * queue: their CUDA-event times; n_info = number of times a search let go of its SM at the end of a quantum
  * (mod 100000) + 100000 * (CTA width of the search kernel) */
 int avp_last_search_passes(avp_ctx *ctx, float *ms_dijkstra, float *ms_search, int32_t *n_info);
+/* batches larger than two waves of wide CTAs are searched by two launches (narrow CTAs give every scenario a few pops and finish the
+ * short searches; the wide launch resumes the rest from the run queue): CUDA-event time of the narrow launch, part of ms_search */
+int avp_last_narrow_ms(avp_ctx *ctx, float *ms);
 
 /* development aids: an in-kernel watchdog (SM clock cycles per scenario, 0 = off; a scenario
  * that exceeds it ends with AVP_CAPACITY) and the per-scenario progress checkpoints

@@ -416,6 +416,9 @@ def test_root_expansion_boundary_rule_matches_oracle(device_planner, cfg):
     {"AVP_QUANTUM": "5", "AVP_FORCE_YIELD": "1", "AVP_SLOTS": "3"},                 # ... with a slot pool that runs dry: fresh scenarios go to the back of the queue
     {"AVP_QUANTUM": "16", "AVP_FORCE_YIELD": "1", "AVP_PLAN_BLOCK": "256"},         # two 256-thread CTAs per SM
     {"AVP_QUANTUM": "64", "AVP_SPREAD": "0"},
+    {"AVP_TWO_PHASE": "1", "AVP_NARROW_BUDGET": "5"},                               # the narrow first launch (128-thread CTAs, 5 pops each), then the wide one
+    {"AVP_TWO_PHASE": "1", "AVP_NARROW_BUDGET": "9", "AVP_SLOTS": "4", "AVP_QUANTUM": "33", "AVP_FORCE_YIELD": "1"},
+    {"AVP_TWO_PHASE": "0"},
 ])
 def test_results_do_not_depend_on_the_scheduling(device_planner, cfg, monkeypatch, env):
     """Suspend / resume (run queue, slot pool, save areas of the heap heads), CTA width and SM-pair placement are scheduling only:
@@ -429,6 +432,6 @@ def test_results_do_not_depend_on_the_scheduling(device_planner, cfg, monkeypatc
     _, _, n_suspend, block = dp.last_search_passes()
     for k, sc in enumerate(scs):
         _compare_plan(dp, res, k, sc, cfg)
-    if "AVP_FORCE_YIELD" in env:
-        assert n_suspend > 100
+    if "AVP_FORCE_YIELD" in env or env.get("AVP_TWO_PHASE") == "1":
+        assert n_suspend > (100 if "AVP_FORCE_YIELD" in env else 5)
     assert block == int(env.get("AVP_PLAN_BLOCK", 512))

@@ -32,3 +32,16 @@ for nm, idx in (("long (20000 pops)", np.where(s["n_pops"] >= 20000)[0]), ("mid 
     tot = float(s["n_pops"][idx].sum())
     print("%-18s total pops %.0f" % ("", tot))
 dp.close()
+
+# wall-clock view: when was every scenario first taken, when did it finish, how long did it hold an SM (light build, prof[10..13])
+t0 = pr[:, 11][pr[:, 11] > 0].min()
+take = (pr[:, 11] - t0) / 1e6; fin = (pr[:, 12] - t0) / 1e6; on_ms = pr[:, 10] / 1.965e6; segs = pr[:, 13]
+long_ = np.where(s["n_pops"] >= 20000)[0]; mid = np.where((s["n_pops"] >= 1024) & (s["n_pops"] < 20000))[0]
+print("kernel span %.1f ms (first take-over to last finish)" % fin.max())
+for nm, idx in (("long", long_), ("mid", mid)):
+    if len(idx) == 0: continue
+    print("%-5s n %3d | first taken at %.1f..%.1f ms | finished at %.1f..%.1f ms (mean %.1f) | held an SM %.1f..%.1f ms (mean %.1f) | waited (finish - take - on SM) mean %.1f max %.1f ms | run segments mean %.1f" %
+          (nm, len(idx), take[idx].min(), take[idx].max(), fin[idx].min(), fin[idx].max(), fin[idx].mean(), on_ms[idx].min(), on_ms[idx].max(), on_ms[idx].mean(),
+           (fin[idx] - take[idx] - on_ms[idx]).mean(), (fin[idx] - take[idx] - on_ms[idx]).max(), segs[idx].mean()))
+order = np.argsort(-fin)[:8]
+print("last finishers: " + "  ".join("#%d pops %d fin %.0f onSM %.0f take %.0f" % (i, s["n_pops"][i], fin[i], on_ms[i], take[i]) for i in order))

@@ -34,13 +34,13 @@ for c in configs:
         ms = dp.plan_resident(256, 0)
         a, b, nsus, blk = dp.last_search_passes()
         if it and (best is None or ms < best[0]):
-            best = (ms, a, b, nsus, blk)
+            best = (ms, a, b, nsus, blk, dp.last_narrow_ms())
     res = dp.fetch(256, 0)
     s = res.summaries
     if base is None:
         base = s.copy()
     same = np.array_equal(base, s)
     hist = np.bincount(s["status"], minlength=7)
-    print("%-4s %-44s search %8.1f ms (dijkstra %6.1f + plan %8.1f) suspends %6d block %d successors %d M/s %.2f same_as_first %s hist %s" %
-          (name, c or "(defaults)", best[0], best[1], best[2], best[3], best[4], res.successors, res.successors / best[0] / 1e3, same, hist.tolist()), flush=True)
+    print("%-4s %-44s search %8.1f ms (dijkstra %6.1f + plan %8.1f, narrow %6.1f) suspends %6d block %d successors %d M/s %.2f same_as_first %s hist %s" %
+          (name, c or "(defaults)", best[0], best[1], best[2], best[5], best[3], best[4], res.successors, res.successors / best[0] / 1e3, same, hist.tolist()), flush=True)
 dp.close()
