@@ -886,6 +886,91 @@ __device__ __forceinline__ void oh_pop_fix_warp(double *sf, int32_t *si, OEnt *g
   if (lane == 0) oh_siftdown<SMO>(sf, si, ge, nodes, pos, fi, item);
   __syncwarp();
 }
+// heapq._siftdown(heap, 0, pos), WARP-COLLECTIVE: the ancestors of `pos` are known before any of them is read, so lane l reads
+// ancestor l + 1 -- every level of the sift in ONE round trip --, the ballot of (item < ancestor) gives the number k of levels the
+// item rises (the serial loop stops at the first ancestor that is not larger), lanes 0..k-1 move their ancestor one level down
+// and lane k writes the item.  Same reads (each ancestor before it is overwritten), same writes as the serial loop.
+// `fi` / `item` / `pos` must be the same on every lane; every lane of the warp calls.
+#ifndef AVP_SERIAL_PUSH
+template <int SMO>
+__device__ __forceinline__ void oh_siftdown_warp(double *sf, int32_t *si, OEnt *ge, Node *nodes, int pos, double fi, int item, int lane) {
+  const int anc = (lane < 30) ? (((pos + 1) >> (lane + 1)) - 1) : -1;
+  double pf = 0.0; int pi = 0;
+  if (anc >= 0) oh_get<SMO>(sf, si, ge, anc, pf, pi);
+  const unsigned up = __ballot_sync(AVP_FULL_MASK, anc >= 0 && fi < pf);
+  const int k = __ffs(~up) - 1;                 // lanes 30, 31 never vote: ~up != 0
+  const int dst = ((pos + 1) >> lane) - 1;      // ancestor `lane` of pos (ancestor 0 = pos itself)
+  if (lane < k) { OH_SET(dst, pf, pi); }
+  else if (lane == k) { OH_SET(dst, fi, item); }
+  __syncwarp();
+}
+#else
+template <int SMO>
+__device__ __forceinline__ void oh_siftdown_warp(double *sf, int32_t *si, OEnt *ge, Node *nodes, int pos, double fi, int item, int lane) {
+  if (lane == 0) oh_siftdown<SMO>(sf, si, ge, nodes, pos, fi, item);
+  __syncwarp();
+}
+#endif
+template <int SMO>
+__device__ __forceinline__ void oh_push_warp(double *sf, int32_t *si, OEnt *ge, Node *nodes, int &n, double f, int idx, int lane) {
+  const int pos = n++;
+  oh_siftdown_warp<SMO>(sf, si, ge, nodes, pos, f, idx, lane);
+}
+// heapq.heappop after the root has been read, HYBRID: while the five levels below the position lie in the shared-memory head the
+// warp takes them in one round (31 sibling pairs compared at once, as oh_pop_fix_warp: two rounds cover the 11 levels of a
+// 2048-entry head); below the head lane 0 descends level by level behind the four-level prefetch (there the 62 scattered loads
+// of a warp round cost more than they save); the final _siftdown (the moved item rising again -- in an A* open list it is a
+// recent push with a small f and rises far) is the warp-collective one.
+template <int SMO>
+__device__ __forceinline__ void oh_pop_fix_hybrid(double *sf, int32_t *si, OEnt *ge, Node *nodes, int n_before, int lane) {
+  const int last = n_before - 1;
+  if (last == 0) return;
+  double fi = 0.0; int item = 0;
+  if (lane == 0) oh_get<SMO>(sf, si, ge, last, fi, item);
+  int pos = 0;
+  bool bottom = false;
+#ifndef AVP_SERIAL_POP_HEAD
+  while (((pos + 1) << 5) + 30 < SMO) {
+    const int d = 32 - __clz(lane + 1), q = lane + 1 - (1 << (d - 1));
+    const int L = ((pos + 1) << d) - 1 + 2 * q;
+    const bool have = lane < 31 && L < last, have_r = have && L + 1 < last;
+    double lf = 0.0, rf = 0.0; int li = 0, ri = 0;
+    if (have) { lf = sf[L]; li = si[L]; }
+    if (have_r) { rf = sf[L + 1]; ri = si[L + 1]; }
+    const bool right = have_r && !(lf < rf);
+    const double cf = right ? rf : lf; const int ci = right ? ri : li;
+    const unsigned vm = __ballot_sync(AVP_FULL_MASK, have), rm = __ballot_sync(AVP_FULL_MASK, right);
+    int node = pos, qq = 0, depth = 0, my_parent = -1;
+#pragma unroll
+    for (int dd = 1; dd <= 5; ++dd) {
+      const int lid = (1 << (dd - 1)) - 1 + qq;
+      if (depth != dd - 1 || !((vm >> lid) & 1u)) break;
+      if (lid == lane) my_parent = node;
+      const int r = (rm >> lid) & 1u;
+      node = ((pos + 1) << dd) - 1 + 2 * qq + r; qq = 2 * qq + r; depth = dd;
+    }
+    if (my_parent >= 0) { sf[my_parent] = cf; si[my_parent] = ci; nodes[ci].hpos = my_parent; }
+    __syncwarp();
+    pos = node;
+    if (depth < 5) { bottom = true; break; }
+  }
+#endif
+  if (!bottom) {
+    if (lane == 0) {
+      int child = 2 * pos + 1, lvl = 0;
+      while (child < last) {
+        const int right = child + 1;
+        if (2 * child + 2 >= SMO && (lvl++ & 3) == 0) oh_prefetch_subtree<SMO>(ge, pos, last);
+        double cf; int ci; oh_get<SMO>(sf, si, ge, child, cf, ci);
+        if (right < last) { double rf; int ri; oh_get<SMO>(sf, si, ge, right, rf, ri); if (!(cf < rf)) { child = right; cf = rf; ci = ri; } }
+        OH_SET(pos, cf, ci); pos = child; child = 2 * pos + 1;
+      }
+    }
+    pos = __shfl_sync(AVP_FULL_MASK, pos, 0);
+  }
+  fi = shfl_d(fi, 0); item = __shfl_sync(AVP_FULL_MASK, item, 0);
+  oh_siftdown_warp<SMO>(sf, si, ge, nodes, pos, fi, item, lane);
+}
 // in-place key update of an entry (hybrid_a_star.py:224-230: no re-heapify)
 template <int SMO>
 __device__ __forceinline__ void oh_set_key(double *sf, OEnt *ge, int hpos, double f) { if (hpos < SMO) sf[hpos] = f; else ge[hpos].f = f; }

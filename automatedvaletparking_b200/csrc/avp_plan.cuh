@@ -339,10 +339,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       if (lane == 0 && go) do_pop();
       __syncwarp();
       const int n_before = s_sift_n;
-#ifdef AVP_WARP_POP
+#if defined(AVP_WARP_POP)
       if (n_before > 0) oh_pop_fix_warp<SMO>(s_of, s_oi, oge, nodes, n_before, lane);
-#else
+#elif defined(AVP_SERIAL_POP)
       if (n_before > 0 && lane == 0) { int n_ = n_before; oh_pop_fix<SMO>(s_of, s_oi, oge, nodes, n_); }
+#else
+      if (n_before > 0) oh_pop_fix_hybrid<SMO>(s_of, s_oi, oge, nodes, n_before, lane);
 #endif
       __syncwarp();
     };
@@ -601,13 +603,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
             while (todo) {
               const int k = __ffs(todo) - 1; todo &= todo - 1;
               const double fk = shfl_d(fv, k);
-              if (lane == 0) {
-                if ((push_m >> k) & 1u) {
-                  LPROF(const long long tl_ = clock_ordered();)
-                  oh_push<SMO>(s_of, s_oi, oge, nodes, on, fk, s_G + k + 1);
-                  LPROF(s_lp[8] += clock_ordered() - tl_; s_lp[9] += 1;)
-                } else oh_set_key<SMO>(s_of, oge, nodes[s_found[k]].hpos, fk);
-              }
+              if ((push_m >> k) & 1u) {                 // every lane: the sift is warp-collective (oh_siftdown_warp)
+                LPROF(long long tl_ = 0; if (lane == 0) tl_ = clock_ordered();)
+                oh_push_warp<SMO>(s_of, s_oi, oge, nodes, on, fk, s_G + k + 1, lane);
+                LPROF(if (lane == 0) { s_lp[8] += clock_ordered() - tl_; s_lp[9] += 1; })
+              } else { if (lane == 0) oh_set_key<SMO>(s_of, oge, nodes[s_found[k]].hpos, fk); __syncwarp(); }
             }
             i = nchild;
           }
