@@ -40,7 +40,8 @@ struct avp_ctx {
   Node *d_nodes = nullptr; OEnt *d_oheap = nullptr; int32_t *d_htab = nullptr; unsigned long long *d_dheap = nullptr;
   ScenState *d_state = nullptr; PlanCtl *d_ctl = nullptr; int32_t *d_queue = nullptr, *d_slot_ring = nullptr; int q_mask = 0, slot_mask = 0;
   int32_t *d_order = nullptr;      // processing order: expensive scenarios (far start-goal pairs) first
-  double *d_course = nullptr; int32_t *d_course_dir = nullptr;
+  double *d_course = nullptr; int32_t *d_course_dir = nullptr; unsigned char *d_cand = nullptr;
+  int narrow_block = 64, narrow64_per_sm = 1;
   int plan_block = 512, plan_grid = 0, ctas_per_sm[2] = {1, 2}, narrow_per_sm = 1; float narrow_ms = 0.f; cudaEvent_t evN = nullptr;
   // results
   avp_plan_summary *d_sums = nullptr; double *d_paths = nullptr; int32_t *d_pops = nullptr, *d_hq = nullptr;
@@ -98,11 +99,13 @@ extern "C" int avp_create(int device_id, const avp_config *cfg, avp_ctx **out) {
   cudaFuncSetAttribute(k_plan<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(256, AVP_CELL_SMEM));
   cudaFuncSetAttribute(k_plan<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(640, AVP_CELL_SMEM));
   cudaFuncSetAttribute(k_plan<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(128, 0));
+  cudaFuncSetAttribute(k_plan<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AVP_PLAN_DYN_SMEM(64, 0));
   {
     int o = 0;
     ctx->ctas_per_sm[0] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<512>, 512, AVP_PLAN_DYN_SMEM(512, AVP_CELL_SMEM)) == cudaSuccess && o > 0) ? o : 1;
     ctx->ctas_per_sm[1] = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<256>, 256, AVP_PLAN_DYN_SMEM(256, AVP_CELL_SMEM)) == cudaSuccess && o > 0) ? o : 1;
     ctx->narrow_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<128>, 128, AVP_PLAN_DYN_SMEM(128, 0)) == cudaSuccess && o > 0) ? o : 1;
+    ctx->narrow64_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_plan<64>, 64, AVP_PLAN_DYN_SMEM(64, 0)) == cudaSuccess && o > 0) ? o : 1;
   }
   ctx->slots = ctx->n_sm * ctx->ctas_per_sm[0];               // persistent grids: multiples of the SM count
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evM); cudaEventCreate(&ctx->evN);
@@ -125,7 +128,7 @@ static void free_results(avp_ctx *ctx) {
 }
 static void free_ws(avp_ctx *ctx) {
   free_dev(ctx->d_nshot); free_dev(ctx->d_nodes); free_dev(ctx->d_oheap); free_dev(ctx->d_htab); free_dev(ctx->d_dheap);
-  free_dev(ctx->d_state); free_dev(ctx->d_ctl); free_dev(ctx->d_queue); free_dev(ctx->d_slot_ring); free_dev(ctx->d_course); free_dev(ctx->d_course_dir);
+  free_dev(ctx->d_state); free_dev(ctx->d_ctl); free_dev(ctx->d_queue); free_dev(ctx->d_slot_ring); free_dev(ctx->d_course); free_dev(ctx->d_course_dir); free_dev(ctx->d_cand); ctx->d_cand = nullptr;
   ctx->d_nshot = nullptr; ctx->d_nodes = nullptr; ctx->d_oheap = nullptr; ctx->d_htab = nullptr; ctx->d_dheap = nullptr; ctx->d_state = nullptr; ctx->d_ctl = nullptr;
   ctx->d_queue = ctx->d_slot_ring = nullptr; ctx->d_course = nullptr; ctx->d_course_dir = nullptr; ctx->ws_n = ctx->ws_slots = ctx->ws_ctas = 0;
 }
@@ -385,6 +388,7 @@ static int ensure_ws(avp_ctx *ctx, int ctas) {
   CK(cudaMalloc(&ctx->d_queue, sizeof(int32_t) * ring)); ctx->q_mask = ring - 1;
   CK(cudaMalloc(&ctx->d_course, sizeof(double) * (size_t)ctas * 3 * AVP_COURSE_CAP));
   CK(cudaMalloc(&ctx->d_course_dir, sizeof(int32_t) * (size_t)ctas * AVP_COURSE_CAP));
+  CK(cudaMalloc(&ctx->d_cand, (size_t)ctas * AVP_CAND_SMEM));
   const size_t slot_bytes = (sizeof(Node) + sizeof(NodeShot) + sizeof(OEnt)) * (size_t)node_cap + sizeof(int32_t) * (size_t)hb;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
@@ -466,7 +470,10 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   // unfinished search goes to the run queue, and the wide launch resumes them (stream order: no host round trip, nothing re-planned).
   bool two_phase = ctx->n > 2 * ctx->n_sm;
   { const char *te = getenv("AVP_TWO_PHASE"); if (te) two_phase = atoi(te) != 0; }
-  int grid_n = ctx->n_sm * ctx->narrow_per_sm; if (grid_n > ctx->n) grid_n = ctx->n;
+  // the narrow CTAs: 64 threads (commit warp + one evaluator warp, eight CTAs per SM: as many Dijkstra warps) or 128 threads (three per SM)
+  int nblock = 64;
+  { const char *ne = getenv("AVP_NARROW_BLOCK"); if (ne && (atoi(ne) == 64 || atoi(ne) == 128)) nblock = atoi(ne); }
+  int grid_n = ctx->n_sm * (nblock == 64 ? ctx->narrow64_per_sm : ctx->narrow_per_sm); if (grid_n > ctx->n) grid_n = ctx->n;
   {
     int need = ctx->n_sm * ctx->ctas_per_sm[1] > grid ? ctx->n_sm * ctx->ctas_per_sm[1] : grid;
     if (grid_n > need) need = grid_n;
@@ -478,7 +485,7 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
   P.n_scen = ctx->n; P.scen = ctx->d_scen; P.cost = ctx->d_cost; P.cells = ctx->d_cells; P.col_start = ctx->d_col;
   P.hval = ctx->d_hval; P.ost = ctx->d_ost; P.gx = ctx->d_gx; P.gy = ctx->d_gy;
   P.dheap = ctx->d_dheap; P.dheap_cap = ctx->dheap_cap; P.nodes = ctx->d_nodes; P.node_cap = ctx->node_cap; P.oheap = ctx->d_oheap; P.nshot = ctx->d_nshot;
-  P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.htab_stride = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir;
+  P.htab = ctx->d_htab; P.htab_size = ctx->htab_size; P.htab_stride = ctx->htab_size; P.course = ctx->d_course; P.course_dir = ctx->d_course_dir; P.cand_scratch = ctx->d_cand;
   P.sums = ctx->d_sums; P.paths = ctx->d_paths; P.cap_path = ctx->cap_path; P.pops = ctx->cap_pops > 0 ? ctx->d_pops : nullptr; P.cap_pops = ctx->cap_pops;
   P.pop_fgh = nullptr;
   if (ctx->trace_fgh && ctx->cap_pops > 0) {
@@ -513,7 +520,9 @@ static int launch_search(avp_ctx *ctx, float *elapsed_ms) {
     PlanParams P1 = PP;
     P1.phase = 1; P1.cell_smem = 0; P1.K.spread = 0;
     { const char *be = getenv("AVP_NARROW_BUDGET"); P1.quantum = (be && atoi(be) > 0) ? atoi(be) : 128; }
-    k_plan<128><<<grid_n, 128, AVP_PLAN_DYN_SMEM(128, 0), ctx->stream>>>(P1); ctx->launches++;
+    if (nblock == 64) k_plan<64><<<grid_n, 64, AVP_PLAN_DYN_SMEM(64, 0), ctx->stream>>>(P1);
+    else k_plan<128><<<grid_n, 128, AVP_PLAN_DYN_SMEM(128, 0), ctx->stream>>>(P1);
+    ctx->launches++;
     PP.phase = 2;
   }
   CK(cudaEventRecord(ctx->evN, ctx->stream));

@@ -336,7 +336,17 @@ __device__ __noinline__ bool check_distance_warp_sm(const VehDims vd, const Scen
   veh_geom_sm(vd, x, y, cs, sn, sg);
   const double x_min = sg->x_min, x_max = sg->x_max, y_min = sg->y_min, y_max = sg->y_max;
   int lo, hi;
+#ifdef AVP_EXACT_COLS
   col_range(S, x_min, x_max, lo, hi);
+#else
+  {   // a superset of the columns the rectangle touches (see check_distance_multi_sm: the per-cell AABB test below is the exact filter)
+    const int nx = S.nx;
+    double fa = floor((x_min - S.b[0]) * S.inv_stepx) - 1.0, fb = floor((x_max - S.b[0]) * S.inv_stepx) + 1.0;
+    if (!(fa >= 0.0)) fa = 0.0; if (!(fb <= (double)(nx - 1))) fb = (double)(nx - 1);
+    if (fa > fb) return false;
+    lo = (int)fa; hi = (int)fb;
+  }
+#endif
   if (lo > hi) return false;
   const int beg = col_start[lo], end = col_start[hi + 1];
   bool hit = false;
@@ -346,6 +356,77 @@ __device__ __noinline__ bool check_distance_warp_sm(const VehDims vd, const Scen
     if (i < end) {
       const double2 p = cells[i];
       if (p.x >= x_min && p.x <= x_max && p.y >= y_min && p.y <= y_max) h = cell_hits(*sg, p.x, p.y);
+    }
+    if (__any_sync(AVP_FULL_MASK, h)) { hit = true; break; }
+  }
+  return hit;
+}
+
+// Up to AVP_MULTI_POSE poses in ONE pass over the cell list: distance_checker.check(pose_0) or ... or check(pose_{np-1}) -- the
+// sub-steps of one successor (hybrid_a_star.py:185-204: any hit decides), a few neighbouring points of a goal-shot course
+// (:334-347, likewise).  Lanes 4p .. 4p+3 hold pose p (x, y, cos, sin) and compute its rectangle side by side (the latency of one
+// pose, same IEEE operations as veh_geom); the cell loop runs once over a SUPERSET of the columns any rectangle touches and tests a
+// cell against the union box first.  A cell takes part in check(pose) iff it passes that pose's inclusive AABB filter
+// (get_near_obstacles, collision_check.py:55-69), which is tested per cell here exactly as there -- so the column range only has
+// to cover the rectangles, it does not have to be the exact one of col_range.
+#define AVP_MULTI_POSE 4
+__device__ __noinline__ bool check_distance_multi_sm(const VehDims vd, const ScenDev &S, const double2 *cells, const int32_t *col_start,
+                                                     int np, double x, double y, double cs, double sn, VehGeom *sgs) {
+  const int lane = threadIdx.x & 31, l = lane & 3, p = lane >> 2;
+  const bool act = p < np;
+  VehGeom *sg = sgs + (act ? p : 0);
+  __syncwarp();                                   // the previous call's readers are done
+  if (act) {
+    const double locx = (l == 0 || l == 3) ? vd.lx0 : vd.lx1, locy = (l < 2) ? vd.ly0 : vd.ly1;
+    const double cx = __fma_rn(-sn, locy, cs * locx) + x;      // as veh_geom
+    const double cy = __fma_rn(cs, locy, sn * locx) + y;
+    sg->vb[l][0] = cx; sg->vb[l][1] = cy;
+    if (l == 0) { sg->vb[4][0] = cx; sg->vb[4][1] = cy; }
+  }
+  __syncwarp();
+  if (act) {
+    const double p1x = sg->vb[l][0], p1y = sg->vb[l][1], p2x = sg->vb[l + 1][0], p2y = sg->vb[l + 1][1];   // vb[4] = vb[0]
+    const double lk = (p2y - p1y) / (p2x - p1x);
+    const double lb = p1y - lk * p1x;
+    const double ls = sqrt(1 + lk * lk);
+    sg->lk[l] = lk; sg->lb[l] = lb; sg->ls[l] = ls; sg->ils[l] = 1.0 / ls;
+    if (l < 2) {                                  // the two side lengths (collision_check.py:165-169)
+      const double d0 = (l == 0) ? sg->vb[0][0] - sg->vb[3][0] : sg->vb[3][0] - sg->vb[2][0];
+      const double d1 = (l == 0) ? sg->vb[0][1] - sg->vb[3][1] : sg->vb[3][1] - sg->vb[2][1];
+      const double side = sqrt(d0 * d0 + d1 * d1);
+      if (l == 0) sg->v_lb = side; else sg->v_len = side;
+    }
+    const int dim = l >> 1; const bool want_max = (l & 1) != 0;    // lane 0: x_min, 1: x_max, 2: y_min, 3: y_max (the strict compare chain of veh_geom)
+    double v = sg->vb[0][dim];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) { const double w = sg->vb[i][dim]; if (want_max ? (w > v) : (w < v)) v = w; }
+    if (l == 0) sg->x_min = v; else if (l == 1) sg->x_max = v; else if (l == 2) sg->y_min = v; else sg->y_max = v;
+  }
+  __syncwarp();
+  double ux0 = sgs[0].x_min, ux1 = sgs[0].x_max, uy0 = sgs[0].y_min, uy1 = sgs[0].y_max;       // union box: a filter only
+  for (int q = 1; q < np; ++q) {
+    const double a = sgs[q].x_min, b = sgs[q].x_max, c = sgs[q].y_min, d = sgs[q].y_max;
+    if (a < ux0) ux0 = a; if (b > ux1) ux1 = b; if (c < uy0) uy0 = c; if (d > uy1) uy1 = d;
+  }
+  // columns: one more than the estimate on either side (a column is S.stepx wide, the estimate is good to 1e-9 columns)
+  const int nx = S.nx;
+  double fa = floor((ux0 - S.b[0]) * S.inv_stepx) - 1.0, fb = floor((ux1 - S.b[0]) * S.inv_stepx) + 1.0;
+  if (!(fa >= 0.0)) fa = 0.0; if (!(fb <= (double)(nx - 1))) fb = (double)(nx - 1);
+  if (fa > fb) return false;                      // every rectangle lies beside the raster
+  const int lo = (int)fa, hi = (int)fb;
+  const int beg = col_start[lo], end = col_start[hi + 1];
+  bool hit = false;
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    bool h = false;
+    if (i < end) {
+      const double2 c = cells[i];
+      if (c.x >= ux0 && c.x <= ux1 && c.y >= uy0 && c.y <= uy1) {
+        for (int q = 0; q < np && !h; ++q) {
+          const VehGeom &g = sgs[q];
+          if (c.x >= g.x_min && c.x <= g.x_max && c.y >= g.y_min && c.y <= g.y_max) h = cell_hits(g, c.x, c.y);
+        }
+      }
     }
     if (__any_sync(AVP_FULL_MASK, h)) { hit = true; break; }
   }
@@ -452,6 +533,7 @@ __device__ __forceinline__ bool rs_LSR(double x, double y, double phi, double sp
 // rs_curve.py:186-197
 __device__ __forceinline__ bool rs_LRL(double x, double y, double phi, double sphi, double cphi, double &t, double &u, double &v) {
   const double X = x - sphi, Y = y - 1.0 + cphi;
+  if (fabs(X) > 4.000001 || fabs(Y) > 4.000001) return false;       // hypot(X, Y) >= max(|X|, |Y|) (1 - 2^-52) > 4: the branch is not taken
   const double u1 = py_hypot(X, Y);
   if (u1 <= 4.0) {
     const double t1 = d_atan2(Y, X);
@@ -466,7 +548,10 @@ __device__ __forceinline__ void rs_tauOmega(double u, double v, double xi, doubl
   double su, cu, sd, cd; d_sincos(u, su, cu); d_sincos(delta, sd, cd);
   const double A = su - sd, B = cu - cd - 1.0;
   const double t1 = d_atan2(eta * A - xi * B, xi * A + eta * B);
-  const double t2 = 2.0 * (cd - d_cos(v) - cu) + 3.0;
+  // both callers pass v = -u or v = u with |u| <= pi/2, and the cos restatement depends on |x| only below 2.426 (avp_cos): cos(v) is
+  // the cos(u) already there, bit for bit
+  const double cv = (fabs(v) == fabs(u) && fabs(u) < 2.0) ? cu : d_cos(v);
+  const double t2 = 2.0 * (cd - cv - cu) + 3.0;
   tau = (t2 < 0) ? rs_M(t1 + AVP_PI) : rs_M(t1);
   omega = rs_M(tau - u + v - phi);
 }

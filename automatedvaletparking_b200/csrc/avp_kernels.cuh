@@ -55,6 +55,7 @@ struct KParams {
   int htab_stride;                // entries between two slots' tables
   double *course;                 // 3*AVP_COURSE_CAP doubles per CTA (scratch)
   int32_t *course_dir;
+  unsigned char *cand_scratch;      // per CTA: the word candidates of the successors (AVP_CAND_SMEM bytes) for CTAs too narrow to keep them in shared memory
   // results per scenario
   avp_plan_summary *sums;
   double *paths; int cap_path;
@@ -999,4 +1000,4 @@ enum { CTL_RUN = 0, CTL_EXIT = 1 };
 #ifndef AVP_SMO_WIDE
 #define AVP_SMO_WIDE 2048
 #endif
-__host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? AVP_SMO_WIDE : 1024; }   // more shared memory here costs L1 hit rate (libm tables, nodes)
+__host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? AVP_SMO_WIDE : (block >= 128 ? 1024 : 512); }   // more shared memory here costs L1 hit rate (libm tables, nodes)

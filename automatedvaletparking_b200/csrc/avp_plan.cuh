@@ -76,8 +76,13 @@ __device__ __forceinline__ void ring_push(int *tail, int32_t *buf, int mask, int
 #ifndef AVP_CELL_SMEM
 #define AVP_CELL_SMEM (48 * 1024)
 #endif
+#ifndef AVP_COURSE_BATCH
+#define AVP_COURSE_BATCH 1      // course points per check item (1 .. AVP_MULTI_POSE); measured: 4 neighbouring points per item +3.5 % step time -- the
+                                // points are checked by different warps at the same time and the first hit ends the scan, a batch only makes the items longer
+#endif
 #define AVP_CAND_SMEM ((int)sizeof(RsCandX) * AVP_NCHILD_MAX * RS_NINST)
-#define AVP_PLAN_DYN_SMEM(block, cell_smem) (12 * avp_sm_open(block) + AVP_CAND_SMEM + (cell_smem))
+#define AVP_CAND_IN_SMEM(block) ((block) >= 128)      // 64-thread CTAs (eight per SM) keep the candidates in global memory (L1 / L2 resident: 40 KB per CTA)
+#define AVP_PLAN_DYN_SMEM(block, cell_smem) (12 * avp_sm_open(block) + (AVP_CAND_IN_SMEM(block) ? AVP_CAND_SMEM : 0) + (cell_smem))
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(AVP_DIJ_WARPS * 32) k_dij_eager(PlanParams P) 
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_plan(PlanParams PP) {
-  static_assert(BLOCK >= 128 && BLOCK % 32 == 0, "one commit warp + at least three evaluator warps");
+  static_assert(BLOCK >= 64 && BLOCK % 32 == 0, "one commit warp + at least one evaluator warp");
   const KParams &P = PP.K;
   constexpr int SMO = avp_sm_open(BLOCK);
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -183,12 +188,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
   __shared__ int s_ctlA, s_ctlB, s_cur, s_do_commit, s_rb, s_nplan, s_npts, s_shot_coll, s_shot_bad, s_work;
   __shared__ int s_G, s_nclosed, s_npops, s_status, s_nhq, s_nhcalls, s_on, s_in_radius, s_best_ok;
   __shared__ int s_work2, s_work3, s_rs_done, s_course_rdy, s_q_rdy, s_sub_rdy, s_ins_done, s_cstride;   // the evaluators' queue: tail counter, finished rs items, course / rs queries / sub-step poses published, table inserts of the running commit done, stride of the course point order
-  __shared__ VehGeom s_vg[BLOCK / 32];           // per warp: the vehicle rectangle of the pose being checked (check_distance_warp_sm)
+  __shared__ VehGeom s_vg[BLOCK / 32][AVP_MULTI_POSE];   // per warp: the vehicle rectangles of the poses being checked (check_distance_multi_sm; [0]: check_distance_warp_sm)
   __shared__ DijCtx s_D;
+  __shared__ __align__(16) ScenDev s_S;
+  __shared__ int s_gcnt[RS_NGROUP];                             // word instances of each ctype group evaluated so far (the warp that completes a group selects its winner)
   __shared__ int s_sift_n;                                      // do_pop: heap size before the pop whose sift the whole commit warp runs (0: none)
   __shared__ __align__(8) unsigned long long s_cell_bar;       // mbarrier of the staged cell list
-  RsCandX (*s_cand)[RS_NINST] = reinterpret_cast<RsCandX (*)[RS_NINST]>(s_dyn + 12 * SMO);   // AVP_CAND_SMEM bytes: word candidates of the successors, with their arranged lengths
-  unsigned char *s_cells = s_dyn + 12 * SMO + AVP_CAND_SMEM;   // PP.cell_smem bytes: double2 cells, then the int32 column starts
+  RsCandX (*s_cand)[RS_NINST] = reinterpret_cast<RsCandX (*)[RS_NINST]>(AVP_CAND_IN_SMEM(BLOCK) ? s_dyn + 12 * SMO : PP.K.cand_scratch + (size_t)blockIdx.x * AVP_CAND_SMEM);   // AVP_CAND_SMEM bytes: word candidates of the successors, with their arranged lengths
+  unsigned char *s_cells = s_dyn + 12 * SMO + (AVP_CAND_IN_SMEM(BLOCK) ? AVP_CAND_SMEM : 0);   // PP.cell_smem bytes: double2 cells, then the int32 column starts
   unsigned cell_parity = 0;
   LPROF(__shared__ long long s_lp[12]; __shared__ long long s_lpe, s_lpc, s_lpt;)
 #ifdef AVP_PROFILE
@@ -264,7 +271,18 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
     NodeShot *nshot = P.nshot + (size_t)(slot < 0 ? 0 : slot) * P.node_cap;
     int32_t *htab = P.htab + (size_t)(slot < 0 ? 0 : slot) * P.htab_stride;
     OEnt *oge = P.oheap + (size_t)(slot < 0 ? 0 : slot) * P.node_cap;
+#ifndef AVP_SCEN_SMEM          // A/B build -DAVP_SCEN_SMEM: the scenario record copied to shared memory (measured 1 % slower than the L1-resident global record)
     const ScenDev &S = P.scen[sc];
+#else
+    // the scenario record in shared memory: col_range / lin_at / map_index / the Dijkstra read its fields on every call, and an L1
+    // miss there (the nodes, heaps and h tables stream through L1) is a round trip to L2 in the middle of a dependent chain
+    {
+      const int32_t *src = reinterpret_cast<const int32_t *>(&P.scen[sc]); int32_t *dst = reinterpret_cast<int32_t *>(&s_S);
+      for (int i = tid; i < (int)(sizeof(ScenDev) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ScenDev &S = s_S;
+#endif
     const double2 *cells = P.cells + S.cell_off;
     const int32_t *col_start = P.col_start + S.col_off;
     const unsigned cell_bytes = (unsigned)S.n_obs * (unsigned)sizeof(double2), col_bytes = (((unsigned)S.nx + 1u) * 4u + 15u) & ~15u;
@@ -512,6 +530,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         SUBT(6);
         if (s_ctlB == CTL_RUN) {
           if (lane < nchild) { s_valid[lane] = 0ull; s_chit[lane] = 0; }
+          if (lane < RS_NGROUP) s_gcnt[lane] = 0;
           if (lane == 0) {
             s_nplan = 0; s_npts = 0; s_cstride = 1; s_work = 0; s_work2 = 0; s_work3 = 0; s_rs_done = 0; s_course_rdy = 0; s_q_rdy = 0; s_sub_rdy = 0;
             s_ins_done = 0; s_shot_coll = 0; s_shot_bad = 0;
@@ -679,6 +698,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[5] += t_ - s_lpt; s_lpt = t_; })
         if (lane == 0) s_sift_n = 0;
         do_pop_warp(s_do_commit || s_status != 0);
+#ifndef AVP_NO_AB_PREFETCH
+        // the serial section after the next barrier A reads the popped node's record and, when the node after it is the heap's new
+        // root, that node's record and stored word: both ids are known now, the loads land while the evaluation finishes
+        if (lane < 4 && s_ctlA == CTL_RUN) {
+          const int a = (lane < 2) ? s_cur : ((s_on > 0) ? s_oi[0] : -1);
+          if (a >= 0) { if (lane & 1) prefetch_l1(&nshot[a]); else prefetch_l1(&nodes[a]); }
+        }
+#endif
         LPROF(if (tid == 0) { const long long t_ = clock_ordered(); s_lp[7] += t_ - s_lpt; s_lpt = t_; })
         WP_ACC(2);
         TS(4);
@@ -709,8 +736,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
       {
         const int phi_np = !T.is_root;             // the root's theta is a Python float (see oracle generate_path)
         const int nsubs = cfg.n_substeps;
+#ifdef AVP_SUB_FINE
+        const int n_items = 4 + RS_NITEM + nchild * nsubs;      // A/B build: one sub-step check per item
+#else
         const int n_items = 4 + RS_NITEM + nchild;
-        VehGeom *vg = &s_vg[warp];
+#endif
+        VehGeom *vg = s_vg[warp];
         for (;;) {
           int it = 0;
           if (lane == 0) it = atomicAdd(&s_work, 1);
@@ -784,7 +815,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               // neighbourhood is free, so a colliding course is found after fewer checks than in path order (any hit decides)
               int st = 1;
 #ifndef AVP_NO_CSTRIDE
-              if (npts > 4) { st = (npts * 49 + 64) >> 7; for (;;) { int a = npts, b = st; while (b) { const int t_ = a % b; a = b; b = t_; } if (a == 1) break; ++st; } }
+              const int nq = (npts + AVP_COURSE_BATCH - 1) / AVP_COURSE_BATCH;      // the unit of the order is a batch of neighbouring points
+              if (nq > 4) { st = (nq * 49 + 64) >> 7; for (;;) { int a = nq, b = st; while (b) { const int t_ = a % b; a = b; b = t_; } if (a == 1) break; ++st; } }
 #endif
               s_npts = npts; s_cstride = st; __threadfence_block(); st_release_cta(&s_course_rdy, 1);
             }
@@ -846,12 +878,30 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
           } else if (it <= 3 + RS_NITEM) {
             const int rs_it = it - 4;
 #endif
-            if (!wait_ge_cta(&s_q_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
             const int k = lane / nchild, row = lane - k * nchild;
             const int inst = (k < 3) ? rs_item_inst[rs_it][k] : -1;
+#ifdef AVP_RS_OWNQ
+            // A/B build: every rs item derives the normalised query of its rows itself (the same operations as item 1, so the same bits)
+            // instead of waiting for item 1 to publish them: the eleven warps that start with an rs item do not idle through item 1
+            RsQuery Qown;
+            if (inst >= 0) {
+              double q0[3];
+              const double tn = cfg.tan_steer[row % cfg.steering_angle_num];
+              const double speed = (row < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+              const double td = speed * cfg.dt;
+              q0[2] = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
+              double cs, sn; d_sincos(q0[2], sn, cs);
+              q0[0] = T.x + td * cs; q0[1] = T.y + td * sn;
+              rs_query_cs(q0, cs, sn, goal, maxc, Qown);
+            }
+            const RsQuery &Qrow = Qown;
+#else
+            if (!wait_ge_cta(&s_q_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
+            const RsQuery &Qrow = s_Q[row];
+#endif
             if (inst >= 0) {
               double t, u, v;
-              if (rs_eval_instance(inst, s_Q[row], t, u, v)) {
+              if (rs_eval_instance(inst, Qrow, t, u, v)) {
                 RsCandX &c = s_cand[row][inst];                       // arranged once, here (rs_curve.py:200-534), and kept for the selection
                 double l[5], a[5]; int ct; unsigned mask;
                 const int n = rs_arrange(inst, t, u, v, 1, 1, l, ct, mask);
@@ -862,6 +912,37 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               }
             }
             __syncwarp();
+#ifdef AVP_SEL_GROUPED       // A/B build (measured +6 % step time: 10 lanes per group selection instead of 22, and the selection code a second time in the hot path)
+            // set_path + calc_optimal_path per ctype group (rs_curve.py:137-156, :99-110) as soon as the group's last instance is there:
+            // the warp that completes a group (a counter per group) selects its winner for every successor (lanes = successors).  The
+            // selection used to follow ALL rs items (11 k cycles at the end of the evaluation, most warps idle); what is left for
+            // the end is the combination of the 11 group winners per successor.
+            {
+              unsigned sel = 0u;
+              if (lane == 0) {
+                __threadfence_block();
+                int gprev = -1, cnt = 0;
+                for (int k2 = 0; k2 <= 3; ++k2) {
+                  const int in2 = (k2 < 3) ? rs_item_inst[rs_it][k2] : -1;
+                  int g2 = -1;
+                  if (in2 >= 0) { g2 = 0; while (in2 >= rs_grp_begin[g2 + 1]) ++g2; }
+                  if (g2 != gprev) {
+                    if (gprev >= 0) { const int old = atomicAdd(&s_gcnt[gprev], cnt); if (old + cnt == rs_grp_begin[gprev + 1] - rs_grp_begin[gprev]) sel |= 1u << gprev; }
+                    gprev = g2; cnt = 0;
+                  }
+                  if (g2 >= 0) ++cnt;
+                }
+                __threadfence_block();
+              }
+              sel = __shfl_sync(AVP_FULL_MASK, sel, 0);
+              __syncwarp();
+              while (sel) {
+                const int g = __ffs(sel) - 1; sel &= sel - 1;
+                if (lane < nchild) rs_select_group_x(s_cand[lane], *(volatile unsigned long long *)&s_valid[lane], g, maxc, s_grp[lane][g]);
+              }
+              __syncwarp();
+            }
+#endif
             if (lane == 0) { __threadfence_block(); add_release_cta(&s_rs_done, 1); }
           } else {
             if (!wait_ge_cta(&s_sub_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; break; }
@@ -870,6 +951,64 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
 #else
             const int i = it - 4 - RS_NITEM;
 #endif
+#if !defined(AVP_SUB_COARSE) && !defined(AVP_SUB_FINE)
+            // the sub-steps of successor i in ONE pass over the cell list (check_distance_multi_sm): their rectangles are computed side by
+            // side by lanes 4p .. 4p+3, any hit decides (hybrid_a_star.py:185-204 breaks at the first one; the flag is an OR)
+            {
+              int coll = 0;
+              if (cfg.collision_mode == 1) {
+                for (int k = nsubs - 1; k >= 0 && !coll; --k) {
+                  const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+                  const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+                  const double td_i = speed * cfg.ddt * (k + 1);
+                  const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+                  double cs, sn; d_sincos(th_i, sn, cs);
+                  coll = check_circle_warp(cfg, S, cells, T.x + td_i * cs, T.y + td_i * sn, cs, sn) ? 1 : 0;
+                }
+              } else {
+                const VehDims vd = veh_dims(cfg);
+                for (int k0 = 0; k0 < nsubs && !coll; k0 += AVP_MULTI_POSE) {
+                  const int np = (nsubs - k0 < AVP_MULTI_POSE) ? nsubs - k0 : AVP_MULTI_POSE;
+                  const int k = k0 + (lane >> 2);
+                  double px = 0.0, py = 0.0, pcs = 1.0, psn = 0.0;
+                  if ((lane >> 2) < np) {
+                    if (k < 4) { px = s_sub[i][k][0]; py = s_sub[i][k][1]; pcs = s_sub[i][k][2]; psn = s_sub[i][k][3]; }
+                    else {
+                      const double tn = cfg.tan_steer[i % cfg.steering_angle_num];
+                      const double speed = (i < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+                      const double td_i = speed * cfg.ddt * (k + 1);
+                      const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+                      d_sincos(th_i, psn, pcs);
+                      px = T.x + td_i * pcs; py = T.y + td_i * psn;
+                    }
+                  }
+                  coll = check_distance_multi_sm(vd, S, cells, col_start, np, px, py, pcs, psn, vg) ? 1 : 0;
+                }
+              }
+              if (lane == 0) s_chit[i] = coll;
+            }
+#elif defined(AVP_SUB_FINE)
+            // one (successor, sub-step) pair per item, the farthest sub-steps of every successor first (any hit decides,
+            // hybrid_a_star.py:185-204 breaks at the first one; the parent pose is collision free, so the sub-step next to it is the
+            // least likely to hit); a successor that has its hit is not checked again
+            {
+              const int j = i, kk0 = j / nchild, ii = j - kk0 * nchild, k = nsubs - 1 - kk0;
+              const int known = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_chit[ii], 0);
+              if (!known) {
+                bool hit;
+                if (k < 4) hit = check_pose_cs_warp_sm(cfg, S, cells, col_start, s_sub[ii][k][0], s_sub[ii][k][1], s_sub[ii][k][2], s_sub[ii][k][3], vg);
+                else {
+                  const double tn = cfg.tan_steer[ii % cfg.steering_angle_num];
+                  const double speed = (ii < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+                  const double td_i = speed * cfg.ddt * (k + 1);
+                  const double th_i = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.ddt * (k + 1));
+                  double cs, sn; d_sincos(th_i, sn, cs);
+                  hit = check_pose_cs_warp_sm(cfg, S, cells, col_start, T.x + td_i * cs, T.y + td_i * sn, cs, sn, vg);
+                }
+                if (hit && lane == 0) s_chit[ii] = 1;
+              }
+            }
+#else
             int coll = 0;
             for (int kk = 0; kk < nsubs; ++kk) {
               // any hit decides (hybrid_a_star.py:185-204 breaks at the first one): the sub-steps are checked farthest first -- the parent pose
@@ -892,6 +1031,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               if (hit) { coll = 1; break; }
             }
             if (lane == 0) s_chit[i] = coll;
+#endif
           }
 #ifdef AVP_PROFILE
           if (lane == 0 && it < 40) atomicAdd(reinterpret_cast<unsigned long long *>(&s_ic[it]), (unsigned long long)(clock64() - ti_));
@@ -908,7 +1048,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         if (warp == 0) { WP_ACC(3); LPROF(if (tid == 0) s_lpc = clock_ordered();) continue; }
         if (!wait_ge_cta(&s_course_rdy, 1)) { if (lane == 0) s_status = AVP_CAPACITY; continue; }
         const int npts = s_npts, cstride = s_cstride;
-#if defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
+        const int nbat = (npts + AVP_COURSE_BATCH - 1) / AVP_COURSE_BATCH;
+#if defined(AVP_SEL_GROUPED)
+        const int n_sel = 1;                        // the group winners are there (E1): one item combines them, lanes = successors
+#elif defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
         const int n_sel = nchild;
 #else
         const int n_sel = (nchild + 1) / 2;
@@ -930,27 +1073,47 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
           } else if (chk_left) {
             if (lane == 0) it = atomicAdd(&s_work2, 1);
             it = __shfl_sync(AVP_FULL_MASK, it, 0);
-            if (it >= npts) { chk_left = false; continue; }
+            if (it >= nbat) { chk_left = false; continue; }
             kind = 1;
           } else break;
           if (kind == 1) {
-            const int j = (int)(((long long)it * cstride) % npts);
+            const int bq = (int)(((long long)it * cstride) % nbat);
             const int stop = __shfl_sync(AVP_FULL_MASK, *(volatile int *)&s_shot_coll, 0);   // warp-uniform early exit
             if (stop) { chk_left = false; continue; }
-            const double ix = CX[j], iy = CY[j], cm = s_tcs[0], sm = s_tcs[1];
-            const double gx_ = cm * ix + sm * iy + T.x, gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
-            const double gyaw = pi_2_pi(CYAW[j] + T.theta);
-            const double gth = pi_2_pi(gyaw);
-            double gsn, gcs; d_sincos(gth, gsn, gcs);
-            if (check_pose_cs_warp_sm(cfg, S, cells, col_start, gx_, gy_, gcs, gsn, vg)) { if (lane == 0) s_shot_coll = 1; }
+            // AVP_COURSE_BATCH neighbouring course points in one pass over the cell list (lanes 4p .. 4p+3: point p of the batch)
+            const int j0 = bq * AVP_COURSE_BATCH, np = (npts - j0 < AVP_COURSE_BATCH) ? npts - j0 : AVP_COURSE_BATCH;
+            const int j = j0 + (lane >> 2);
+            double gx_ = 0.0, gy_ = 0.0, gsn = 0.0, gcs = 1.0;
+            if ((lane >> 2) < np) {
+              const double ix = CX[j], iy = CY[j], cm = s_tcs[0], sm = s_tcs[1];
+              gx_ = cm * ix + sm * iy + T.x; gy_ = -sm * ix + cm * iy + T.y;      // rs_curve.py:124-130
+              const double gyaw = pi_2_pi(CYAW[j] + T.theta);
+              const double gth = pi_2_pi(gyaw);
+              d_sincos(gth, gsn, gcs);
+            }
+            bool chit = false;
+            if (cfg.collision_mode == 1) {
+              for (int q = 0; q < np && !chit; ++q)
+                chit = check_circle_warp(cfg, S, cells, shfl_d(gx_, 4 * q), shfl_d(gy_, 4 * q), shfl_d(gcs, 4 * q), shfl_d(gsn, 4 * q));
+            }
+#if AVP_COURSE_BATCH == 1 && defined(AVP_COURSE_SINGLE)     // A/B build: the single-pose function (a second copy of the cell predicate in the hot code: +4 % step time)
+            else chit = check_distance_warp_sm(veh_dims(cfg), S, cells, col_start, shfl_d(gx_, 0), shfl_d(gy_, 0), shfl_d(gcs, 0), shfl_d(gsn, 0), vg);
+#else
+            else chit = check_distance_multi_sm(veh_dims(cfg), S, cells, col_start, np, gx_, gy_, gcs, gsn, vg);
+#endif
+            if (chit) { if (lane == 0) s_shot_coll = 1; }
           } else {
-#if defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
+#if defined(AVP_SEL_GROUPED)
+            const int gl = 0, i = lane;
+#elif defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
             const int gl = lane, i = (lane < 16) ? it : nchild;
 #else
             const int half = lane >> 4, gl = lane & 15, i = 2 * it + half;
 #endif
+#ifndef AVP_SEL_GROUPED
             if (i < nchild && gl < RS_NGROUP) rs_select_group_x(s_cand[i], s_valid[i], gl, maxc, s_grp[i][gl]);
             __syncwarp();
+#endif
             if (i < nchild && gl == 0) {
               // calc_optimal_path over the group winners in order (rs_curve.py:99-110: the last word with L <= min wins)
               int bi = -1, degenerate = 0; double minL = 0.0;

@@ -45,3 +45,11 @@ for nm, idx in (("long", long_), ("mid", mid)):
            (fin[idx] - take[idx] - on_ms[idx]).mean(), (fin[idx] - take[idx] - on_ms[idx]).max(), segs[idx].mean()))
 order = np.argsort(-fin)[:8]
 print("last finishers: " + "  ".join("#%d pops %d fin %.0f onSM %.0f take %.0f" % (i, s["n_pops"][i], fin[i], on_ms[i], take[i]) for i in order))
+# what becomes of the 10 successors of a pop (long searches): pushed, closed on creation (collision), found again in the open list
+# (key update or not), skipped (found in the closed list / out of bounds)
+li = np.where(s["n_pops"] >= 20000)[0]
+if len(li):
+    G = s["global_index"][li].astype(np.float64); pops_ = s["n_pops"][li].astype(np.float64)
+    pushed = s["n_open"][li] + pops_; coll = s["n_closed"][li] - pops_; upd = s["n_hcalls"][li] - pushed; skip = G - pushed - coll - upd
+    print("successors per pop (long): pushed %.2f  collided %.2f  found open %.2f  skipped (closed / out of bounds) %.2f" %
+          ((pushed / pops_).mean(), (coll / pops_).mean(), (upd / pops_).mean(), (skip / pops_).mean()))
