@@ -623,6 +623,13 @@ __device__ __forceinline__ void rs_query_cs(const double q0[3], double c, double
   Q.sp = sp; Q.cp = cp;
   Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;          // rs_curve.py:286-287, :456-457
 }
+// the same with sin / cos of dth = q1[2] - q0[2] supplied by the caller (k_plan evaluates them beside sin / cos of q0[2], on other lanes)
+__device__ __forceinline__ void rs_query_cs2(const double q0[3], double c, double s, const double q1[3], double maxc, double sp, double cp, RsQuery &Q) {
+  const double dx = q1[0] - q0[0], dy = q1[1] - q0[1], dth = q1[2] - q0[2];
+  Q.x = (c * dx + s * dy) * maxc; Q.y = (-s * dx + c * dy) * maxc; Q.phi = dth;
+  Q.sp = sp; Q.cp = cp;
+  Q.xb = Q.x * cp + Q.y * sp; Q.yb = Q.x * sp - Q.y * cp;
+}
 __device__ __forceinline__ void rs_query(const double q0[3], const double q1[3], double maxc, RsQuery &Q) {
   double s0, c0; d_sincos(q0[2], s0, c0);
   rs_query_cs(q0, c0, s0, q1, maxc, Q);

@@ -45,7 +45,16 @@ enum { CTL_FINISH = 2 };
 // that a warp runs one word formula where possible (4 instances per family: 3 + 1 left over).  Ordered by measured cost,
 // longest first (profiles/: 21 k ... 3 k cycles per item); a left-over item with three different formulas costs the sum of
 // the three (41 k cycles for {9,29,37}), so those instances are items of their own.
-#ifndef AVP_RS_FINE
+#if !defined(AVP_RS_BYCOST) && !defined(AVP_RS_FINE)
+// The items of one word family next to each other in the queue (two warps run the same formula code at the same time: the
+// instruction lines they fetch are shared), the left-over fourth instance of each family as an item of its own.  Measured against
+// the cost-ordered 19-item table below (-DAVP_RS_BYCOST): C3 -2.3 %, C2 within the noise.
+#define RS_NITEM 23
+__device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
+  {6, 7, 8}, {9, -1, -1}, {26, 27, 28}, {29, -1, -1}, {34, 35, 36}, {37, -1, -1}, {30, 31, 32}, {33, -1, -1}, {38, 39, 40}, {41, -1, -1},
+  {42, 43, 44}, {45, -1, -1}, {10, 11, 12}, {13, -1, -1}, {14, 15, 16}, {17, -1, -1}, {2, 3, 4}, {5, -1, -1},
+  {20, 21, -1}, {18, 19, -1}, {22, 23, -1}, {24, 25, -1}, {0, 1, -1}};
+#elif !defined(AVP_RS_FINE)
 #define RS_NITEM 19
 __device__ __constant__ int8_t rs_item_inst[RS_NITEM][3] = {
   {45, 13, 17}, {0, 1, -1}, {6, 7, 8}, {5, 33, 41}, {20, 21, -1}, {22, 23, -1}, {10, 11, 12}, {14, 15, 16}, {26, 27, 28},

@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               s_npts = npts; s_cstride = st; __threadfence_block(); st_release_cta(&s_course_rdy, 1);
             }
           } else if (it == 1) {
+#ifdef AVP_QUERY_SERIAL      // A/B build: two sin/cos evaluations one after the other on lanes 0..nchild-1
             if (lane < nchild) {
               const int c = lane;
               double q0[3];
@@ -833,6 +834,29 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               W.cpose[c][0] = q0[0]; W.cpose[c][1] = q0[1]; W.cpose[c][2] = q0[2];
               rs_query_cs(q0, cs, sn, goal, maxc, s_Q[c]);
             }
+#else
+            // successor c: lane c evaluates sin / cos of its heading, lane 16 + c sin / cos of (goal heading - its heading) at the same
+            // time (one call of the same function on 2 * nchild lanes instead of two calls one after the other: the start of every
+            // evaluation waits for this item); same arguments, same bits
+            {
+              const int c = lane & 15, half = lane >> 4;
+              double th = 0.0, sv = 0.0, cv = 1.0;
+              if (c < nchild) {
+                const double tn = cfg.tan_steer[c % cfg.steering_angle_num];
+                th = pi_2_pi(T.theta + (cfg.max_v * tn) / cfg.lw * cfg.dt);
+                d_sincos(half ? (goal[2] - th) : th, sv, cv);
+              }
+              const double sp = shfl_d(sv, (lane & 15) + 16), cp = shfl_d(cv, (lane & 15) + 16);
+              if (lane < nchild) {
+                double q0[3];
+                const double speed = (c < nchild / 2.0) ? cfg.max_v : -cfg.max_v;
+                const double td = speed * cfg.dt;
+                q0[2] = th; q0[0] = T.x + td * cv; q0[1] = T.y + td * sv;
+                W.cpose[c][0] = q0[0]; W.cpose[c][1] = q0[1]; W.cpose[c][2] = q0[2];
+                rs_query_cs2(q0, cv, sv, goal, maxc, sp, cp, s_Q[c]);
+              }
+            }
+#endif
             __syncwarp();
             if (lane == 0) { __threadfence_block(); st_release_cta(&s_q_rdy, 1); }
           } else if (it == 2) {

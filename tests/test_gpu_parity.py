@@ -416,7 +416,8 @@ def test_root_expansion_boundary_rule_matches_oracle(device_planner, cfg):
     {"AVP_QUANTUM": "5", "AVP_FORCE_YIELD": "1", "AVP_SLOTS": "3"},                 # ... with a slot pool that runs dry: fresh scenarios go to the back of the queue
     {"AVP_QUANTUM": "16", "AVP_FORCE_YIELD": "1", "AVP_PLAN_BLOCK": "256"},         # two 256-thread CTAs per SM
     {"AVP_QUANTUM": "64", "AVP_SPREAD": "0"},
-    {"AVP_TWO_PHASE": "1", "AVP_NARROW_BUDGET": "5"},                               # the narrow first launch (128-thread CTAs, 5 pops each), then the wide one
+    {"AVP_TWO_PHASE": "1", "AVP_NARROW_BUDGET": "5"},                               # the narrow first launch (64-thread CTAs, 5 pops each), then the wide one
+    {"AVP_TWO_PHASE": "1", "AVP_NARROW_BUDGET": "40", "AVP_NARROW_BLOCK": "128"},   # ... with 128-thread narrow CTAs (word candidates in shared memory)
     {"AVP_TWO_PHASE": "1", "AVP_NARROW_BUDGET": "9", "AVP_SLOTS": "4", "AVP_QUANTUM": "33", "AVP_FORCE_YIELD": "1"},
     {"AVP_TWO_PHASE": "0"},
 ])
