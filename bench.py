@@ -417,9 +417,11 @@ def run_workload(name, dp, rank, world, local_rank, W, K, n_c2, with_clocks, cpu
                          "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                          "kernel": "k_plan", "model": "sum((12*N_obs+63.2)*successors) per launch (SURVEY 8d)",
                          "fp64_pipe_pct": kc.get(name, {}).get("fp64_pipe_pct"), "issue_slots_pct": kc.get(name, {}).get("issue_slots_pct"),
+                         "icc_hit_pct": kc.get(name, {}).get("icc_hit_pct"), "ipc_per_active_sm": kc.get(name, {}).get("ipc_per_active_sm"),
                          "counters_from": kc.get(name, {}).get("source"),
-                         "reading": "the kernel is latency bound (strictly ordered pops of bit-exact fp64 libm chains), not HBM bound: measured DRAM "
-                                    "traffic is far below the algorithmic bytes of the model"},
+                         "reading": "the kernel is latency and instruction-fetch bound (strictly ordered pops of bit-exact fp64 libm chains from ~117 KB of "
+                                    "hot code against a 32 KB instruction cache: icc hit rate 64 %, 0.7 instructions per cycle on a busy SM), not "
+                                    "HBM bound: measured DRAM traffic is far below the algorithmic bytes of the model"},
         }
         if clk is not None:
             out["clocks"] = clk

@@ -10,7 +10,8 @@ want = ['Kernel Name', 'Block Size', 'Grid Size', 'gpu__time_duration.sum', 'dra
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio', 'sass__inst_executed_local_loads',
-        'sass__inst_executed_local_stores', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__cycles_active.avg']
+        'sass__inst_executed_local_stores', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__cycles_active.avg',
+        'sm__icc_request_hit_rate.pct', 'sm__inst_issued.avg.per_cycle_active']
 with open(sys.argv[2], 'w') as f:
     f.write('metric,unit,value\n')
     for h, u, v in zip(hdr, units, vals):
