@@ -519,6 +519,12 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
   const int nx = S.nx, ny = S.ny, mx = S.mx, my = S.my, stride = S.stride, n_ids = S.n_ids;
   int hn = D.hn, closed_len = D.closed_len, status = 0;
   const double inv_dx = 1.0 / dx, inv_dy = 1.0 / dy;
+  // heappop walks five levels per round (below): lane -> sibling pair q of level d under the current position (lane 31: none), the
+  // lanes holding the pair's ancestors inside the round (pl_anc) and those of them that have to choose their RIGHT child for the pair
+  // to lie on the path (pl_want) -- constants of the lane
+  const int pl_d = 32 - __clz(lane + 1), pl_q = lane + 1 - (1 << (pl_d - 1));
+  unsigned pl_anc = 0u, pl_want = 0u;
+  for (int k = 1; k < pl_d && pl_d <= 5; ++k) { const int a = (1 << (k - 1)) - 1 + (pl_q >> (pl_d - k)); pl_anc |= 1u << a; if ((pl_q >> (pl_d - k - 1)) & 1) pl_want |= 1u << a; }
 
 #define HP_GET(i) ((i) < AVP_SM_HEAP ? sheap[(i)] : gheap[(i)])
 #define HP_SET(i, v) do { if ((i) < AVP_SM_HEAP) sheap[(i)] = (v); else gheap[(i)] = (v); } while (0)
@@ -571,11 +577,11 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
     while (todo) {                            // in the reference's neighbour order
       const int k = __ffs(todo) - 1; todo &= todo - 1;
       const unsigned long long key_k = shfl_u64(key, k);
-      if ((pm >> k) & 1u) {                   // heappush
-        if (lane == 0) {
-          if (hn >= gcap) status = AVP_CAPACITY;
-          else {
-            int pos = hn++;
+      if ((pm >> k) & 1u) {                   // heappush (hn and status are tracked by every lane: no broadcast after the loop)
+        if (hn >= gcap) status = AVP_CAPACITY;
+        else {
+          if (lane == 0) {
+            int pos = hn;
             while (pos > 0) {                 // heapq._siftdown
               const int parent = (pos - 1) >> 1;
               const unsigned long long pv = HP_GET(parent);
@@ -584,9 +590,10 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
             }
             HP_SET(pos, key_k);
           }
+          hn++;
         }
       } else {                                // overwrite IN PLACE, no re-sift (:222-228)
-        const int hn_b = __shfl_sync(AVP_FULL_MASK, hn, 0);
+        const int hn_b = hn;
         __syncwarp();
         int pos = 0x7fffffff;
         for (int i = lane; i < hn_b; i += 32) if ((unsigned)HP_GET(i) == (unsigned)key_k) { pos = i; break; }
@@ -595,13 +602,11 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
         __syncwarp();
       }
     }
-    hn = __shfl_sync(AVP_FULL_MASK, hn, 0);
-    status = __shfl_sync(AVP_FULL_MASK, status, 0);
+    __syncwarp();                               // lane 0's heap writes are visible to the warp
     if (status) break;
     if (hn == 0) { status = AVP_H_UNREACHABLE; break; }
     // update_closedlist (:74-82): heappop
-    unsigned long long top = (lane == 0) ? sheap[0] : 0ull;
-    top = shfl_u64(top, 0);
+    const unsigned long long top = sheap[0];      // every lane reads the root (a shared-memory broadcast)
     const int cur_id = (int)(unsigned)top;
     const double nxt_x = gxa[cur_id], nxt_y = gya[cur_id];     // issued before the sift so that the latency overlaps it
     // the popped cell is expanded next: its neighbours' state words and cost-map bytes are prefetched while lane 0 sifts (the
@@ -645,28 +650,25 @@ __device__ __forceinline__ int dij_compute_path(DijCtx &D, unsigned long long *s
       if (n > 0) {
         int pos = 0;
         for (;;) {
-          const int d = 32 - __clz(lane + 1), q = lane + 1 - (1 << (d - 1));          // lane -> pair q of level d (lane 31: none)
-          const long long L = (((long long)pos + 1) << d) - 1 + 2 * q;
+          const int L = ((pos + 1) << pl_d) - 1 + 2 * pl_q;                              // left entry of this lane's pair
           const bool have = lane < 31 && L < n, have_r = have && L + 1 < n;
           unsigned long long lv = 0ull, rv = 0ull;
-          if (have) lv = HP_GET((int)L);
-          if (have_r) rv = HP_GET((int)L + 1);
+          if (have) lv = HP_GET(L);
+          if (have_r) rv = HP_GET(L + 1);
           const bool right = have_r && !(lv < rv);
           const unsigned long long cv = right ? rv : lv;
-          const unsigned vm = __ballot_sync(AVP_FULL_MASK, have), rm = __ballot_sync(AVP_FULL_MASK, right);
-          int node = pos, qq = 0, depth = 0, my_parent = -1;
-#pragma unroll
-          for (int dd = 1; dd <= 5; ++dd) {
-            const int lid = (1 << (dd - 1)) - 1 + qq;
-            if (depth != dd - 1 || !((vm >> lid) & 1u)) break;
-            if (lid == lane) my_parent = node;                                          // this lane's pair hangs below the path
-            const int r = (rm >> lid) & 1u;
-            node = (int)((((long long)pos + 1) << dd) - 1 + 2 * qq + r); qq = 2 * qq + r; depth = dd;
-          }
-          if (my_parent >= 0) HP_SET(my_parent, cv);
+          const unsigned rm = __ballot_sync(AVP_FULL_MASK, right);
+          // the pair lies on the path iff it exists and every ancestor pair chose the child it hangs below: one mask compare per lane
+          // instead of walking the five levels one after the other (an existing pair's ancestors exist)
+          const bool on = have && ((rm & pl_anc) == pl_want);
+          const unsigned om = __ballot_sync(AVP_FULL_MASK, on);
+          if (on) HP_SET(((pos + 1) << (pl_d - 1)) - 1 + pl_q, cv);                     // the winner moves up to the pair's parent
           __syncwarp();
-          pos = node;
-          if (depth < 5) break;                                                          // a leaf
+          if (om == 0u) break;                                                           // no child: a leaf
+          const int t = 31 - __clz(om);                                                  // the deepest pair on the path (lane ids grow with the level)
+          const int dt = 32 - __clz(t + 1), qt = t + 1 - (1 << (dt - 1));
+          pos = ((pos + 1) << dt) - 1 + 2 * qt + (int)((rm >> t) & 1u);
+          if (dt < 5) break;                                                             // the path ended inside the round: a leaf
         }
         if (lane == 0) {
           while (pos > 0) {                     // heapq._siftdown(heap, 0, pos)
@@ -931,8 +933,12 @@ __device__ __forceinline__ void oh_pop_fix_hybrid(double *sf, int32_t *si, OEnt 
   int pos = 0;
   bool bottom = false;
 #ifndef AVP_SERIAL_POP_HEAD
+  // lane -> sibling pair q of level d below the position; the pair lies on the path iff it exists and every ancestor pair of the round
+  // chose the child it hangs below: one mask compare per lane (as in dij_compute_path)
+  const int d = 32 - __clz(lane + 1), q = lane + 1 - (1 << (d - 1));
+  unsigned anc = 0u, want = 0u;
+  for (int k = 1; k < d && d <= 5; ++k) { const int a = (1 << (k - 1)) - 1 + (q >> (d - k)); anc |= 1u << a; if ((q >> (d - k - 1)) & 1) want |= 1u << a; }
   while (((pos + 1) << 5) + 30 < SMO) {
-    const int d = 32 - __clz(lane + 1), q = lane + 1 - (1 << (d - 1));
     const int L = ((pos + 1) << d) - 1 + 2 * q;
     const bool have = lane < 31 && L < last, have_r = have && L + 1 < last;
     double lf = 0.0, rf = 0.0; int li = 0, ri = 0;
@@ -940,20 +946,15 @@ __device__ __forceinline__ void oh_pop_fix_hybrid(double *sf, int32_t *si, OEnt 
     if (have_r) { rf = sf[L + 1]; ri = si[L + 1]; }
     const bool right = have_r && !(lf < rf);
     const double cf = right ? rf : lf; const int ci = right ? ri : li;
-    const unsigned vm = __ballot_sync(AVP_FULL_MASK, have), rm = __ballot_sync(AVP_FULL_MASK, right);
-    int node = pos, qq = 0, depth = 0, my_parent = -1;
-#pragma unroll
-    for (int dd = 1; dd <= 5; ++dd) {
-      const int lid = (1 << (dd - 1)) - 1 + qq;
-      if (depth != dd - 1 || !((vm >> lid) & 1u)) break;
-      if (lid == lane) my_parent = node;
-      const int r = (rm >> lid) & 1u;
-      node = ((pos + 1) << dd) - 1 + 2 * qq + r; qq = 2 * qq + r; depth = dd;
-    }
-    if (my_parent >= 0) { sf[my_parent] = cf; si[my_parent] = ci; nodes[ci].hpos = my_parent; }
+    const unsigned rm = __ballot_sync(AVP_FULL_MASK, right);
+    const bool on = have && ((rm & anc) == want);
+    const unsigned om = __ballot_sync(AVP_FULL_MASK, on);
+    if (on) { const int par = ((pos + 1) << (d - 1)) - 1 + q; sf[par] = cf; si[par] = ci; nodes[ci].hpos = par; }
     __syncwarp();
-    pos = node;
-    if (depth < 5) { bottom = true; break; }
+    if (om == 0u) { bottom = true; break; }
+    const int t = 31 - __clz(om), dt = 32 - __clz(t + 1), qt = t + 1 - (1 << (dt - 1));
+    pos = ((pos + 1) << dt) - 1 + 2 * qt + (int)((rm >> t) & 1u);
+    if (dt < 5) { bottom = true; break; }
   }
 #endif
   if (!bottom) {
