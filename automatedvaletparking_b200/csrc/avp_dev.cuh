@@ -50,7 +50,9 @@ __device__ __noinline__ double d_cos(double x) { return avp_cos(x); }
 #ifdef AVP_NO_SINCOS     // A/B build: two calls
 __device__ __forceinline__ void d_sincos(double x, double &s, double &c) { s = d_sin(x); c = d_cos(x); }
 #else
-__device__ __noinline__ void d_sincos(double x, double &s, double &c) { s = avp_sin(x); c = avp_cos(x); }
+// (the pair comes back in registers: reference parameters of an out-of-line function live in local memory)
+__device__ __noinline__ double2 d_sincos_v(double x) { double2 r; r.x = avp_sin(x); r.y = avp_cos(x); return r; }
+__device__ __forceinline__ void d_sincos(double x, double &s, double &c) { const double2 r = d_sincos_v(x); s = r.x; c = r.y; }
 #endif
 __device__ __noinline__ double d_atan2(double y, double x) { return avp_atan2(y, x); }
 __device__ __noinline__ double d_asin(double x) { return avp_asin(x); }
@@ -111,18 +113,25 @@ __device__ __forceinline__ double py_mod(double v, double w) {
 
 // CPython 3.12 sum() over a list whose element i is an np.float64 iff bit i of npmask is set
 // (see oracle/avp_oracle.c py_sum for the derivation)
+// Written as ONE fully unrolled loop over the (at most five) elements with constant indices, so that an array the caller fills with
+// constant indices stays in registers: the compensated phase runs until the first np.float64 element (or the end), its correction is
+// applied there, the rest is added naively -- the same operations in the same order as the two loops of the derivation.
 __device__ __forceinline__ double py_sum(const double *v, int n, unsigned npmask) {
   double f = 0.0 + v[0], c = 0.0;
-  int i = 1;
-  if (!(npmask & 1u)) {
-    for (; i < n && !(npmask & (1u << i)); ++i) {
-      double x = v[i], t = f + x;
-      if (fabs(f) >= fabs(x)) c += (f - t) + x; else c += (x - t) + f;
-      f = t;
+  bool comp = !(npmask & 1u);
+#pragma unroll
+  for (int i = 1; i < 5; ++i) {
+    if (i < n) {
+      const double x = v[i];
+      if (comp && (npmask & (1u << i))) { if (c != 0.0 && isfinite(c)) f += c; comp = false; }
+      if (comp) {
+        const double t = f + x;
+        if (fabs(f) >= fabs(x)) c += (f - t) + x; else c += (x - t) + f;
+        f = t;
+      } else f = f + x;
     }
-    if (c != 0.0 && isfinite(c)) f += c;
   }
-  for (; i < n; ++i) f = f + v[i];
+  if (comp && c != 0.0 && isfinite(c)) f += c;
   return f;
 }
 
@@ -656,8 +665,8 @@ __device__ __forceinline__ bool rs_eval_instance(int inst, const RsQuery &Q, dou
 }
 
 // instance -> (ctype id, lengths[], n, np-type mask); arrangement per rs_curve.py:200-534
-__device__ __noinline__ int rs_arrange(int inst, double t, double u, double v, int xy_np, int phi_np,
-                                          double *l, int &ct, unsigned &mask) {
+__device__ __forceinline__ int rs_arrange_inl(int inst, double t, double u, double v, int xy_np, int phi_np,
+                                              double *l, int &ct, unsigned &mask) {
   const unsigned P = phi_np ? 1u : 0u;
   if (inst < 2) { l[0] = t; l[1] = u; l[2] = v; ct = inst ? CT_SRS : CT_SLS; mask = (xy_np ? 1u : 0u) | (P << 1); return 3; }
   const int r = (inst - 2) & 3, fam = (inst - 2) >> 2, hi = r >> 1;
@@ -675,6 +684,13 @@ __device__ __noinline__ int rs_arrange(int inst, double t, double u, double v, i
     case 9: l[0] = s * v; l[1] = s * u; l[2] = s * -AVP_HALF_PI; l[3] = s * t; ct = hi ? CT_LSLR : CT_RSRL; mask = P; return 4;
     default: l[0] = s * t; l[1] = s * -AVP_HALF_PI; l[2] = s * u; l[3] = s * -AVP_HALF_PI; l[4] = s * v; ct = hi ? CT_RLSRL : CT_LRSLR; mask = P << 4; return 5;
   }
+}
+
+// out of line for the callers off the hot path (one copy per kernel); the rs items of k_plan inline the body: their length arrays
+// stay in registers
+__device__ __noinline__ int rs_arrange(int inst, double t, double u, double v, int xy_np, int phi_np,
+                                       double *l, int &ct, unsigned &mask) {
+  return rs_arrange_inl(inst, t, u, v, xy_np, phi_np, l, ct, mask);
 }
 
 // Candidate results of the 46 instances (filled in parallel), then the sequential
@@ -743,7 +759,8 @@ __device__ __forceinline__ void rs_select_group_x(const RsCandX *cand, unsigned 
       const RsCandX &o = cand[e];
       if (o.ct != c.ct) continue;
       double d[5];
-      for (int i = 0; i < c.n; ++i) d[i] = o.len[i] - c.len[i];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) d[i] = (i < c.n) ? o.len[i] - c.len[i] : 0.0;
       if (py_sum(d, c.n, c.mask) <= 0.01) { dup = true; break; }     // rs_curve.py:143-146
     }
     if (dup) continue;

@@ -927,9 +927,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               double t, u, v;
               if (rs_eval_instance(inst, Qrow, t, u, v)) {
                 RsCandX &c = s_cand[row][inst];                       // arranged once, here (rs_curve.py:200-534), and kept for the selection
-                double l[5], a[5]; int ct; unsigned mask;
-                const int n = rs_arrange(inst, t, u, v, 1, 1, l, ct, mask);
-                for (int q = 0; q < n; ++q) { a[q] = fabs(l[q]); c.len[q] = l[q]; }
+                double l[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, a[5]; int ct; unsigned mask;
+                const int n = rs_arrange_inl(inst, t, u, v, 1, 1, l, ct, mask);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { a[q] = fabs(l[q]); if (q < n) c.len[q] = l[q]; }
                 c.t = t; c.u = u; c.v = v; c.n = n; c.ct = ct; c.mask = mask;
                 c.L = py_sum(a, n, mask);                              // rs_curve.py:148
                 atomicOr(&s_valid[row], 1ull << inst);
