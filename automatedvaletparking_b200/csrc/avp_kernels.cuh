@@ -999,6 +999,6 @@ enum { CTL_RUN = 0, CTL_EXIT = 1 };
 
 // shared-memory entries of the open heap per CTA width (dynamic shared memory: 12 bytes per entry)
 #ifndef AVP_SMO_WIDE
-#define AVP_SMO_WIDE 2048
+#define AVP_SMO_WIDE 1024      // (2048: C2 +2 % step time together with two successors per selection item; 8192: +3 %)
 #endif
 __host__ __device__ constexpr int avp_sm_open(int block) { return block >= 256 ? AVP_SMO_WIDE : (block >= 128 ? 1024 : 512); }   // more shared memory here costs L1 hit rate (libm tables, nodes)

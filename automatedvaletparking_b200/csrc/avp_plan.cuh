@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         const int nbat = (npts + AVP_COURSE_BATCH - 1) / AVP_COURSE_BATCH;
 #if defined(AVP_SEL_GROUPED)
         const int n_sel = 1;                        // the group winners are there (E1): one item combines them, lanes = successors
-#elif defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
+#elif !defined(AVP_SEL_PAIRED)      // one successor per selection item (lanes = ctype groups); -DAVP_SEL_PAIRED: two successors per item (measured 2 % slower on C2 together with the 2048-entry heap head)
         const int n_sel = nchild;
 #else
         const int n_sel = (nchild + 1) / 2;
@@ -1130,7 +1130,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
           } else {
 #if defined(AVP_SEL_GROUPED)
             const int gl = 0, i = lane;
-#elif defined(AVP_RS_FINE) || defined(AVP_SEL_FINE)
+#elif !defined(AVP_SEL_PAIRED)      // one successor per selection item (lanes = ctype groups); -DAVP_SEL_PAIRED: two successors per item (measured 2 % slower on C2 together with the 2048-entry heap head)
             const int gl = lane, i = (lane < 16) ? it : nchild;
 #else
             const int half = lane >> 4, gl = lane & 15, i = 2 * it + half;
