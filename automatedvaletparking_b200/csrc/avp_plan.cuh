@@ -1065,7 +1065,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
         if (warp != 0) { WP_ACC(1); TS(5); WP_START(); PIPE_TICK(32, 12); }
         // ---- E2: the items that consume other items' results:
         //   course point checks (hybrid_a_star.py:334-347), after s_course_rdy, in strided order, skipped once one of them hit
-        //   word selection, two successors per warp item (lanes 0..10 / 16..26 = ctype groups): set_path de-duplication + minimum
+        //   word selection, one successor per warp item (lanes 0..10 = ctype groups; -DAVP_SEL_PAIRED: two, lanes 0..10 / 16..26): set_path de-duplication + minimum
         //   per group, then calc_optimal_path (combine the groups) and the word kept for the successor's own shot; after every
         //   rs item is finished (s_rs_done).  A warp takes a selection whenever the rs items are finished, else a course point.
         // the commit warp only helps while E1 items are left: it arrives late, and a selection or a course point taken then
