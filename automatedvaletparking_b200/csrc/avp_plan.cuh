@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
   __shared__ int s_work2, s_work3, s_rs_done, s_course_rdy, s_q_rdy, s_sub_rdy, s_ins_done, s_cstride;   // the evaluators' queue: tail counter, finished rs items, course / rs queries / sub-step poses published, table inserts of the running commit done, stride of the course point order
   __shared__ VehGeom s_vg[BLOCK / 32][AVP_MULTI_POSE];   // per warp: the vehicle rectangles of the poses being checked (check_distance_multi_sm; [0]: check_distance_warp_sm)
   __shared__ DijCtx s_D;
+#ifdef AVP_SCEN_SMEM
   __shared__ __align__(16) ScenDev s_S;
+#endif
   __shared__ int s_gcnt[RS_NGROUP];                             // word instances of each ctype group evaluated so far (the warp that completes a group selects its winner)
   __shared__ int s_sift_n;                                      // do_pop: heap size before the pop whose sift the whole commit warp runs (0: none)
   __shared__ __align__(8) unsigned long long s_cell_bar;       // mbarrier of the staged cell list
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK >= 512 ? 1 : 512 / BLOCK)) k_pla
               // them: no insert and no Dijkstra resume has happened since, except that an h value missing then may be there now
               hvp = R.hv[i];
               if (hvp < 0 && id >= 0) hvp = hval[id];
-              const double x_ = R.cpose[i][0], y_ = R.cpose[i][1], th = R.cpose[i][2];
+              const double x_ = R.cpose[i][0], y_ = R.cpose[i][1];
 #ifdef AVP_NO_LOOKAHEAD
               found = htab_find(htab, hmask, nodes, x_, y_, th);
 #else
